@@ -1,0 +1,111 @@
+/* SPDX-License-Identifier: MIT
+ *
+ * sgicp_b200.h -- C-ABI of the B200-native small_gicp hot path (libsgicp_b200.so).
+ *
+ * One context = one GPU = one CUDA stream.  A context is NOT thread-safe; distinct contexts are
+ * (the reference runs several align() calls concurrently from TBB flow-graph nodes,
+ * src/benchmark/odometry_benchmark_small_gicp_tbb_flow.cpp:81-98 -- give each its own context).
+ *
+ * Every entry point returns 0 on success and a non-zero code on failure; sgb_last_error() then
+ * returns a description.  There is NO CPU fallback: without a CUDA device sgb_create() fails.
+ *
+ * All host input buffers are borrowed for the duration of the call only; the context owns all
+ * device memory.  Host layouts are exactly the reference's in-memory layouts so that the header
+ * glue can pass `cloud.points[0].data()` etc. without repacking:
+ *   points / normals : N x 4 doubles (x,y,z,1) / (nx,ny,nz,0)   -- std::vector<Eigen::Vector4d>,
+ *                      include/small_gicp/points/point_cloud.hpp:69-70
+ *   covariances      : N x 16 doubles, 4x4 with zero 4th row/col (symmetric, so row/col-major
+ *                      agree)                                    -- point_cloud.hpp:71
+ *   poses            : 16 doubles, COLUMN-major 4x4 = Eigen::Isometry3d::data()
+ *   H | b | e        : 36 + 6 + 1 doubles (H symmetric)          -- the tuple returned by
+ *                      Reduction::linearize, registration/reduction.hpp:20-27
+ */
+#ifndef SGICP_B200_H_
+#define SGICP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgb_ctx sgb_ctx;
+
+/* Per-point factor evaluated by the kernel.
+ * replaces ICPFactor::linearize/error          include/small_gicp/factors/icp_factor.hpp:20-64
+ *          PointToPlaneICPFactor::linearize/.. include/small_gicp/factors/plane_icp_factor.hpp:20-69
+ *          GICPFactor::linearize/error         include/small_gicp/factors/gicp_factor.hpp:35-89 */
+enum sgb_factor_kind { SGB_FACTOR_ICP = 0, SGB_FACTOR_PLANE_ICP = 1, SGB_FACTOR_GICP = 2 };
+/* RobustFactor<Huber|Cauchy, F>   include/small_gicp/factors/robust_kernel.hpp:11-106 */
+enum sgb_robust_kind { SGB_ROBUST_NONE = 0, SGB_ROBUST_HUBER = 1, SGB_ROBUST_CAUCHY = 2 };
+/* NullRejector / DistanceRejector include/small_gicp/registration/rejector.hpp:11-28 */
+enum sgb_rejector_kind { SGB_REJECT_NONE = 0, SGB_REJECT_DISTANCE = 1 };
+
+#define SGB_NO_CORRESPONDENCE UINT64_MAX /* std::numeric_limits<size_t>::max(), icp_factor.hpp:66 */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sgb_create(int device_id, sgb_ctx** out_ctx);
+void sgb_destroy(sgb_ctx* ctx);
+/* ctx may be NULL: returns the error of the last failed sgb_create() on this thread. */
+const char* sgb_last_error(const sgb_ctx* ctx);
+/* Run all work of this context on an existing cudaStream_t (e.g. the caller's / torch's current
+ * stream) instead of the context's own.  Pass NULL to go back to the private stream. */
+int sgb_set_stream(sgb_ctx* ctx, void* cuda_stream);
+/* Block until everything queued by this context has finished. */
+int sgb_synchronize(sgb_ctx* ctx);
+/* Number of this library's kernels launched by the context since creation (bench.py gpu_launches). */
+uint64_t sgb_kernel_launches(const sgb_ctx* ctx);
+
+/* ---- target: replaces traits::point/normal/cov(target, k) (points/traits.hpp:38-54) and the
+ *      target_tree argument of Reduction::linearize (reduction.hpp:23) -------------------------- */
+int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points_xyz1, const double* normals_xyz0 /*or NULL*/,
+                          const double* covs_4x4 /*or NULL*/);
+/* Adopt a tree built by the reference: `nodes24` = KdTree<PointCloud>::kdtree.nodes.data()
+ * (KdTreeNode<AxisAlignedProjection>, 24 bytes, ann/kdtree.hpp:56-71), `indices` = ...kdtree.indices.data()
+ * (ann/kdtree.hpp:237).  Any builder's node order is accepted (serial / OMP / TBB). Leaf scan order is
+ * preserved, so exact-tie behaviour follows the reference's (ann/knn_result.hpp:80-83). */
+int sgb_target_set_kdtree(sgb_ctx* ctx, const void* nodes24, size_t n_nodes, uint32_t root, const uint64_t* indices);
+/* Or build this library's own kd-tree over the current target points (replaces
+ * KdTreeBuilder::build_tree, ann/kdtree.hpp:74-131).  max_leaf_size <= 0 selects the default (20). */
+int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size);
+/* Gaussian voxel map target (VGICP): replaces IncrementalVoxelMap<GaussianVoxel>::nearest_neighbor_search
+ * (ann/incremental_voxelmap.hpp:99-119) and its point/cov traits (:207-222).  Voxel i of the arrays is
+ * flat_voxels[i]; reported correspondences are (i << 32) like calc_index (:151).
+ * search_offsets is 1, 7 or 27 (:157-186). */
+int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, const int32_t* coords_xyz, const double* means_xyz1,
+                            const double* covs_4x4, int search_offsets);
+size_t sgb_target_size(const sgb_ctx* ctx);
+
+/* ---- source: replaces traits::point/cov(source, i) ------------------------------------------- */
+int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points_xyz1, const double* covs_4x4 /*or NULL*/);
+size_t sgb_source_size(const sgb_ctx* ctx);
+
+/* ---- the hot path ------------------------------------------------------------------------------
+ * sgb_linearize replaces {Serial,ParallelReductionOMP,ParallelReductionTBB}::linearize
+ * (registration/reduction.hpp:20-47, reduction_omp.hpp:24-59, reduction_tbb.hpp:117-131): for every
+ * source point transform -> nearest neighbour -> reject -> factor -> sum.  out_Hbe = H(36) | b(6) | e(1).
+ * The correspondences (and, for GICP, the linearisation pose from which the fused precision matrix is
+ * re-derived) stay cached in the context for sgb_error(), as the reference caches them in its factor
+ * vector (gicp_factor.hpp:94-96). */
+int sgb_linearize(sgb_ctx* ctx, int factor_kind, int robust_kind, double robust_c, int rejector_kind, double max_dist_sq,
+                  const double* T_colmajor16, double* out_Hbe43);
+/* replaces {...}::error (reduction.hpp:55-62, reduction_omp.hpp:61-70, reduction_tbb.hpp:133-138):
+ * sum of factor errors at a trial pose with the cached correspondences (no new search). */
+int sgb_error(sgb_ctx* ctx, const double* T_colmajor16, double* out_e);
+/* Same, but asynchronous on the context's stream with the result left in DEVICE memory
+ * (d_out44 = H|b|e|num_inliers as doubles; d_out1 = e) -- for multi-GPU all-reduce without a host hop. */
+int sgb_linearize_device(sgb_ctx* ctx, int factor_kind, int robust_kind, double robust_c, int rejector_kind, double max_dist_sq,
+                         const double* T_colmajor16, double* d_out44);
+int sgb_error_device(sgb_ctx* ctx, const double* T_colmajor16, double* d_out1);
+
+/* factors[i].target_index of the last linearize, in the caller's source order
+ * (SGB_NO_CORRESPONDENCE = rejected; icp_factor.hpp:66-69). */
+int sgb_correspondences(sgb_ctx* ctx, uint64_t* target_index);
+/* count_if(factors, inlier()) of the last linearize (registration/optimizer.hpp:60,146). */
+int sgb_num_inliers(sgb_ctx* ctx, size_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGICP_B200_H_ */

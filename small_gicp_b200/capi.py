@@ -1,0 +1,210 @@
+"""ctypes binding of include/sgicp_b200.h.  numpy in, numpy out; poses are 4x4 row-major numpy arrays
+(transposed to Eigen's column-major at the boundary)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+FACTOR_ICP, FACTOR_PLANE_ICP, FACTOR_GICP = 0, 1, 2
+ROBUST_NONE, ROBUST_HUBER, ROBUST_CAUCHY = 0, 1, 2
+REJECT_NONE, REJECT_DISTANCE = 0, 1
+NO_CORRESPONDENCE = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/sgicp_b200.h declares
+_SIGNATURES = {
+    "sgb_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "sgb_destroy": (None, [_vp]),
+    "sgb_last_error": (C.c_char_p, [_vp]),
+    "sgb_set_stream": (C.c_int, [_vp, _vp]),
+    "sgb_synchronize": (C.c_int, [_vp]),
+    "sgb_kernel_launches": (C.c_uint64, [_vp]),
+    "sgb_target_set_points": (C.c_int, [_vp, C.c_size_t, _dp, _dp, _dp]),
+    "sgb_target_set_kdtree": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _u64p]),
+    "sgb_target_build_kdtree": (C.c_int, [_vp, C.c_int]),
+    "sgb_target_set_voxelmap": (C.c_int, [_vp, C.c_double, C.c_size_t, _i32p, _dp, _dp, C.c_int]),
+    "sgb_target_size": (C.c_size_t, [_vp]),
+    "sgb_source_set_points": (C.c_int, [_vp, C.c_size_t, _dp, _dp]),
+    "sgb_source_size": (C.c_size_t, [_vp]),
+    "sgb_linearize": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp]),
+    "sgb_error": (C.c_int, [_vp, _dp, _dp]),
+    "sgb_linearize_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _dp, _vp]),
+    "sgb_error_device": (C.c_int, [_vp, _dp, _vp]),
+    "sgb_correspondences": (C.c_int, [_vp, _u64p]),
+    "sgb_num_inliers": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+}
+
+
+class SgbError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libsgicp_b200.so")
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise SgbError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C small_gicp_b200/csrc`). There is no CPU fallback."
+            )
+        L = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _pose(T):
+    T = _f64(T)
+    assert T.shape == (4, 4)
+    return np.ascontiguousarray(T.T)  # row-major transpose == column-major original
+
+
+def _points4(p):
+    p = _f64(p)
+    assert p.ndim == 2 and p.shape[1] in (3, 4)
+    if p.shape[1] == 3:
+        p = np.concatenate([p, np.ones((p.shape[0], 1))], axis=1)
+    return np.ascontiguousarray(p)
+
+
+class Context:
+    """One GPU, one stream (sgb_ctx)."""
+
+    def __init__(self, device=0):
+        self._L = _lib()
+        h = _vp()
+        rc = self._L.sgb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SgbError(self._L.sgb_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SgbError(self._L.sgb_last_error(self._h).decode())
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.sgb_set_stream(self._h, _vp(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def synchronize(self):
+        self._check(self._L.sgb_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.sgb_kernel_launches(self._h))
+
+    # ---- target ----
+    def set_target(self, points, normals=None, covs=None):
+        p = _points4(points)
+        n = _f64(normals) if normals is not None else None
+        c = _f64(covs) if covs is not None else None
+        if n is not None:
+            assert n.shape == (p.shape[0], 4)
+        if c is not None:
+            assert c.shape == (p.shape[0], 4, 4)
+        self._check(self._L.sgb_target_set_points(self._h, p.shape[0], _d(p), _d(n), _d(c)))
+
+    def set_target_kdtree(self, nodes24, indices, root=0):
+        nodes24 = np.ascontiguousarray(nodes24, dtype=np.uint8)
+        indices = np.ascontiguousarray(indices, dtype=np.uint64)
+        self._check(self._L.sgb_target_set_kdtree(self._h, nodes24.ctypes.data_as(_vp), nodes24.shape[0], int(root), indices.ctypes.data_as(_u64p)))
+
+    def build_target_kdtree(self, max_leaf_size=0):
+        self._check(self._L.sgb_target_build_kdtree(self._h, int(max_leaf_size)))
+
+    def set_target_voxelmap(self, leaf_size, coords, means, covs, search_offsets=1):
+        coords = np.ascontiguousarray(coords, dtype=np.int32)
+        m = _points4(means)
+        c = _f64(covs) if covs is not None else None
+        self._check(self._L.sgb_target_set_voxelmap(self._h, float(leaf_size), m.shape[0], coords.ctypes.data_as(_i32p), _d(m), _d(c), int(search_offsets)))
+
+    @property
+    def target_size(self):
+        return int(self._L.sgb_target_size(self._h))
+
+    # ---- source ----
+    def set_source(self, points, covs=None):
+        p = _points4(points)
+        c = _f64(covs) if covs is not None else None
+        if c is not None:
+            assert c.shape == (p.shape[0], 4, 4)
+        self._check(self._L.sgb_source_set_points(self._h, p.shape[0], _d(p), _d(c)))
+
+    @property
+    def source_size(self):
+        return int(self._L.sgb_source_size(self._h))
+
+    # ---- hot path ----
+    def linearize(self, T, factor=FACTOR_GICP, robust=ROBUST_NONE, robust_c=1.0, rejector=REJECT_DISTANCE, max_dist_sq=1.0):
+        """Reduction::linearize -> (H 6x6, b 6, e)"""
+        Tc = _pose(T)
+        out = np.empty(43)
+        self._check(self._L.sgb_linearize(self._h, factor, robust, float(robust_c), rejector, float(max_dist_sq), _d(Tc), _d(out)))
+        return out[:36].reshape(6, 6).copy(), out[36:42].copy(), float(out[42])
+
+    def error(self, T):
+        Tc = _pose(T)
+        e = C.c_double(0.0)
+        self._check(self._L.sgb_error(self._h, _d(Tc), C.byref(e)))
+        return e.value
+
+    def linearize_device(self, T, d_out_ptr, factor=FACTOR_GICP, robust=ROBUST_NONE, robust_c=1.0, rejector=REJECT_DISTANCE, max_dist_sq=1.0):
+        """asynchronous; d_out_ptr = device address of >= 44 doubles (H | b | e | num_inliers)"""
+        Tc = _pose(T)
+        self._check(self._L.sgb_linearize_device(self._h, factor, robust, float(robust_c), rejector, float(max_dist_sq), _d(Tc), _vp(d_out_ptr)))
+
+    def error_device(self, T, d_out_ptr):
+        Tc = _pose(T)
+        self._check(self._L.sgb_error_device(self._h, _d(Tc), _vp(d_out_ptr)))
+
+    def correspondences(self):
+        out = np.empty(self.source_size, dtype=np.uint64)
+        self._check(self._L.sgb_correspondences(self._h, out.ctypes.data_as(_u64p)))
+        return out
+
+    def num_inliers(self):
+        n = C.c_size_t(0)
+        self._check(self._L.sgb_num_inliers(self._h, C.byref(n)))
+        return int(n.value)

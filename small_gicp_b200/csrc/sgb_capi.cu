@@ -1,0 +1,573 @@
+// SPDX-License-Identifier: MIT
+// Context + C-ABI (include/sgicp_b200.h) of the B200-native small_gicp hot path.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sgicp_b200.h"
+#include "sgb_kdtree_host.hpp"
+#include "sgb_kernels.h"
+
+using namespace sgb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;  // slack so streams of slightly varying frames do not realloc
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+}  // namespace
+
+struct sgb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  // ---- target ----
+  size_t n_tgt = 0;
+  bool tgt_has_normals = false, tgt_has_covs = false;
+  bool tgt_is_voxel = false, tgt_ready = false;
+  DevBuf tgt_orig_pts, tgt_orig_normals, tgt_orig_covA, tgt_orig_covB;  // original order
+  DevBuf tgt_pts, tgt_normals, tgt_covA, tgt_covB;                      // leaf order (or voxel order)
+  DevBuf tgt_nodes, tgt_perm;
+  int tree_depth = 0;
+  DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
+  DevBuf vox_table;
+  uint32_t vox_mask = 0;
+  int vox_offsets = 1;
+  double vox_inv_leaf = 1.0;
+
+  // ---- source ----
+  size_t n_src = 0;
+  bool src_has_covs = false;
+  DevBuf src_pts, src_covA, src_covB, src_perm, src_centre, src_bounds;
+
+  // ---- scratch ----
+  DevBuf stage_pts, stage_normals, stage_covs;  // raw double uploads
+  DevBuf tmp_pts, tmp_covA, tmp_covB, keys_in, keys_out, vals_in, sort_temp;
+  DevBuf corr, partials, ticket, out44, corr64;
+  double* h_out = nullptr;  // pinned, 64 doubles
+
+  // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
+  bool have_lin = false;
+  int lin_factor = 0, lin_robust = 0;
+  double lin_c = 1.0;
+  double Tlin[12];
+  const double* last_out = nullptr;  // device pointer holding H|b|e|inliers of the last linearize
+  int lin_grid = 0;
+};
+
+namespace {
+
+int fail(sgb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CU(expr)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return fail(ctx, 2, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+  } while (0)
+
+inline void pose_from_colmajor(const double* T, double out12[12]) {
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) out12[i * 3 + j] = T[j * 4 + i];
+    out12[9 + i] = T[12 + i];
+  }
+}
+
+uint32_t host_vox_hash(int x, int y, int z) {  // must equal vox_hash() in sgb_device.cuh
+  uint32_t h = static_cast<uint32_t>(x) * 73856093u ^ static_cast<uint32_t>(y) * 19349669u ^ static_cast<uint32_t>(z) * 83492791u;
+  h ^= h >> 15;
+  h *= 0x2c1b3c6du;
+  h ^= h >> 12;
+  return h;
+}
+
+int ensure_reduction_buffers(sgb_ctx* ctx, int grid) {
+  CU(ctx->partials.reserve(static_cast<size_t>(grid) * kPartialStride * sizeof(double)));
+  if (!ctx->ticket.p) {
+    CU(ctx->ticket.reserve(sizeof(unsigned int)));
+    CU(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  }
+  CU(ctx->out44.reserve(64 * sizeof(double)));
+  return 0;
+}
+
+int upload_tree(sgb_ctx* ctx, const FlatTree& tree) {
+  CU(ctx->tgt_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
+  CU(ctx->tgt_perm.reserve(tree.perm.size() * sizeof(uint32_t)));
+  CU(cudaMemcpyAsync(ctx->tgt_nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->tgt_perm.p, tree.perm.data(), tree.perm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  const size_t n = ctx->n_tgt;
+  CU(ctx->tgt_pts.reserve(n * sizeof(float4)));
+  if (ctx->tgt_has_normals) CU(ctx->tgt_normals.reserve(n * sizeof(float4)));
+  if (ctx->tgt_has_covs) {
+    CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
+  }
+  CU(launch_gather(ctx->tgt_perm.as<uint32_t>(), n, ctx->tgt_orig_pts.as<float4>(), ctx->tgt_pts.as<float4>(),
+                   ctx->tgt_has_normals ? ctx->tgt_orig_normals.as<float4>() : nullptr, ctx->tgt_normals.as<float4>(),
+                   ctx->tgt_has_covs ? ctx->tgt_orig_covA.as<float4>() : nullptr, ctx->tgt_covA.as<float4>(),
+                   ctx->tgt_has_covs ? ctx->tgt_orig_covB.as<float4>() : nullptr, ctx->tgt_covB.as<float4>(), ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  // the host vectors go out of scope when the caller returns: make sure the async copies are done
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->tree_depth = tree.depth;
+  ctx->tgt_is_voxel = false;
+  ctx->tgt_ready = true;
+  ctx->have_lin = false;
+  return 0;
+}
+
+int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
+  std::memset(&P, 0, sizeof(P));
+  P.tgt.pts = ctx->tgt_pts.as<float4>();
+  P.tgt.normals = ctx->tgt_normals.as<float4>();
+  P.tgt.covA = ctx->tgt_covA.as<float4>();
+  P.tgt.covB = ctx->tgt_covB.as<float4>();
+  P.tgt.nodes = ctx->tgt_nodes.as<KdNode>();
+  P.tgt.centre = ctx->tgt_centre.as<double>();
+  P.tgt.vox_table = ctx->vox_table.as<int4>();
+  P.tgt.vox_mask = ctx->vox_mask;
+  P.tgt.vox_num_offsets = ctx->vox_offsets;
+  P.tgt.vox_inv_leaf = ctx->vox_inv_leaf;
+  P.src.pts = ctx->src_pts.as<float4>();
+  P.src.covA = ctx->src_covA.as<float4>();
+  P.src.covB = ctx->src_covB.as<float4>();
+  P.src.centre = ctx->src_centre.as<double>();
+  P.src.n = static_cast<uint32_t>(ctx->n_src);
+  pose_from_colmajor(T_colmajor16, P.T);
+  P.corr = ctx->corr.as<uint32_t>();
+  P.partials = ctx->partials.as<double>();
+  P.ticket = ctx->ticket.as<unsigned int>();
+  return 0;
+}
+
+int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* d_out) {
+  if (factor < 0 || factor > 2 || robust < 0 || robust > 2 || rejector < 0 || rejector > 1) return fail(ctx, 1, "sgb_linearize: invalid factor/robust/rejector kind");
+  if (!T) return fail(ctx, 1, "sgb_linearize: null pose");
+  CU(cudaSetDevice(ctx->device));
+  ctx->last_out = d_out;
+  if (ctx->n_src == 0 || ctx->n_tgt == 0) {  // empty clouds must not crash (helper_test.cpp:53-59): sum over nothing
+    CU(cudaMemsetAsync(d_out, 0, 44 * sizeof(double), ctx->stream));
+    if (ctx->n_src) {
+      CU(ctx->corr.reserve(ctx->n_src * sizeof(uint32_t)));
+      CU(cudaMemsetAsync(ctx->corr.p, 0xFF, ctx->n_src * sizeof(uint32_t), ctx->stream));
+    }
+    ctx->have_lin = true;
+    ctx->lin_factor = factor;
+    ctx->lin_robust = robust;
+    ctx->lin_c = robust_c;
+    pose_from_colmajor(T, ctx->Tlin);
+    return 0;
+  }
+  if (!ctx->tgt_ready) return fail(ctx, 1, "sgb_linearize: target has no search structure (call sgb_target_set_kdtree / _build_kdtree / _set_voxelmap)");
+  if (factor == SGB_FACTOR_PLANE_ICP && (!ctx->tgt_has_normals || ctx->tgt_is_voxel)) return fail(ctx, 1, "sgb_linearize: point-to-plane needs target normals");
+  if (factor == SGB_FACTOR_GICP && (!ctx->tgt_has_covs || !ctx->src_has_covs)) return fail(ctx, 1, "sgb_linearize: GICP needs target and source covariances");
+
+  const int depth = ctx->tgt_is_voxel ? 0 : (ctx->tree_depth > 0 ? ctx->tree_depth : 1);
+  const int occ = linearize_occupancy(depth);
+  int grid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
+  const int cap = ctx->sm_count * occ;
+  if (grid > cap) grid = cap;
+  if (int rc = ensure_reduction_buffers(ctx, grid)) return rc;
+  CU(ctx->corr.reserve(ctx->n_src * sizeof(uint32_t)));
+
+  LinParams P;
+  fill_params(ctx, P, T);
+  std::memcpy(P.Tlin, P.T, sizeof(P.T));
+  float bound = FLT_MAX;
+  if (rejector == SGB_REJECT_DISTANCE) {
+    bound = nextafterf(static_cast<float>(max_dist_sq), INFINITY);  // accept d2 <= max (rejector.hpp:24 rejects d2 > max)
+    if (!(bound < FLT_MAX)) bound = FLT_MAX;
+  }
+  P.max_dist_sq = bound;
+  P.robust_c = robust_c;
+  P.out = d_out;
+  CU(launch_linearize(P, factor, robust, ctx->tgt_is_voxel, grid, depth, ctx->stream));
+  ctx->launches += 1;
+  ctx->have_lin = true;
+  ctx->lin_factor = factor;
+  ctx->lin_robust = robust;
+  ctx->lin_c = robust_c;
+  ctx->lin_grid = grid;
+  std::memcpy(ctx->Tlin, P.T, sizeof(P.T));
+  return 0;
+}
+
+int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
+  if (!T) return fail(ctx, 1, "sgb_error: null pose");
+  if (!ctx->have_lin) return fail(ctx, 1, "sgb_error: no preceding sgb_linearize (the correspondences are cached there)");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->n_src == 0 || ctx->n_tgt == 0) {
+    CU(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
+    return 0;
+  }
+  int grid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
+  const int cap = ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  if (int rc = ensure_reduction_buffers(ctx, grid)) return rc;
+  LinParams P;
+  fill_params(ctx, P, T);
+  std::memcpy(P.Tlin, ctx->Tlin, sizeof(P.Tlin));
+  P.robust_c = ctx->lin_c;
+  P.out = d_out;
+  CU(launch_error(P, ctx->lin_factor, ctx->lin_robust, grid, ctx->stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int sgb_create(int device_id, sgb_ctx** out_ctx) {
+  if (!out_ctx) return 1;
+  *out_ctx = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("sgb_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                     "); this library has no CPU fallback";
+    return 3;
+  }
+  if (device_id < 0 || device_id >= count) {
+    g_create_error = "sgb_create: device_id out of range";
+    return 1;
+  }
+  e = cudaSetDevice(device_id);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return 2;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device_id);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return 2;
+  }
+  if (prop.major != 10) {
+    g_create_error = "sgb_create: kernels are built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return 3;
+  }
+  sgb_ctx* ctx = new sgb_ctx();
+  ctx->device = device_id;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_out), 64 * sizeof(double));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("sgb_create: ") + cudaGetErrorString(e);
+    delete ctx;
+    return 2;
+  }
+  ctx->stream = ctx->own_stream;
+  *out_ctx = ctx;
+  return 0;
+}
+
+void sgb_destroy(sgb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->tgt_orig_pts, &ctx->tgt_orig_normals, &ctx->tgt_orig_covA, &ctx->tgt_orig_covB, &ctx->tgt_pts,  &ctx->tgt_normals, &ctx->tgt_covA,
+                    &ctx->tgt_covB,     &ctx->tgt_nodes,        &ctx->tgt_perm,      &ctx->tgt_centre,    &ctx->tgt_bounds, &ctx->vox_table, &ctx->src_pts,
+                    &ctx->src_covA,     &ctx->src_covB,         &ctx->src_perm,      &ctx->src_centre,    &ctx->src_bounds, &ctx->stage_pts, &ctx->stage_normals,
+                    &ctx->stage_covs,   &ctx->tmp_pts,          &ctx->tmp_covA,      &ctx->tmp_covB,      &ctx->keys_in,  &ctx->keys_out,    &ctx->vals_in,
+                    &ctx->sort_temp,    &ctx->corr,             &ctx->partials,      &ctx->ticket,        &ctx->out44,    &ctx->corr64};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* sgb_last_error(const sgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sgb_set_stream(sgb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return 1;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return 0;
+}
+
+int sgb_synchronize(sgb_ctx* ctx) {
+  if (!ctx) return 1;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t sgb_kernel_launches(const sgb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+size_t sgb_target_size(const sgb_ctx* ctx) { return ctx ? ctx->n_tgt : 0; }
+size_t sgb_source_size(const sgb_ctx* ctx) { return ctx ? ctx->n_src : 0; }
+
+// ---------------------------------------------------------------------------------------------
+int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points, const double* normals, const double* covs) {
+  if (!ctx) return 1;
+  if (n && !points) return fail(ctx, 1, "sgb_target_set_points: null points");
+  if (n >= (1ull << 31)) return fail(ctx, 1, "sgb_target_set_points: too many points");
+  CU(cudaSetDevice(ctx->device));
+  ctx->n_tgt = n;
+  ctx->tgt_has_normals = normals != nullptr;
+  ctx->tgt_has_covs = covs != nullptr;
+  ctx->tgt_ready = false;
+  ctx->tgt_is_voxel = false;
+  ctx->have_lin = false;
+  CU(ctx->tgt_centre.reserve(4 * sizeof(double)));
+  CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
+  if (n == 0) return 0;
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (normals) {
+    CU(ctx->stage_normals.reserve(n * 4 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->stage_normals.p, normals, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx->tgt_orig_normals.reserve(n * sizeof(float4)));
+  }
+  if (covs) {
+    CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx->tgt_orig_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tgt_orig_covB.reserve(n * sizeof(float4)));
+  }
+  CU(ctx->tgt_orig_pts.reserve(n * sizeof(float4)));
+  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->tgt_bounds.as<double>(), ctx->tgt_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->stage_pts.as<double>(), normals ? ctx->stage_normals.as<double>() : nullptr, covs ? ctx->stage_covs.as<double>() : nullptr, n,
+                    ctx->tgt_centre.as<double>(), ctx->tgt_orig_pts.as<float4>(), ctx->tgt_orig_normals.as<float4>(), ctx->tgt_orig_covA.as<float4>(),
+                    ctx->tgt_orig_covB.as<float4>(), nullptr, nullptr, ctx->sm_count, ctx->stream));
+  ctx->launches += 4;
+  // pageable host memory: the async copies above are staged synchronously, nothing else borrows the inputs
+  return 0;
+}
+
+int sgb_target_set_kdtree(sgb_ctx* ctx, const void* nodes24, size_t n_nodes, uint32_t root, const uint64_t* indices) {
+  if (!ctx) return 1;
+  if (ctx->n_tgt == 0) {
+    ctx->tgt_ready = true;
+    return 0;
+  }
+  if (!nodes24 || !indices) return fail(ctx, 1, "sgb_target_set_kdtree: null tree");
+  CU(cudaSetDevice(ctx->device));
+  double centre[4];
+  CU(cudaMemcpyAsync(centre, ctx->tgt_centre.p, sizeof(centre), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  FlatTree tree;
+  std::string err;
+  if (!flatten_reference_tree(nodes24, n_nodes, root, indices, ctx->n_tgt, centre, tree, err)) return fail(ctx, 1, "sgb_target_set_kdtree: " + err);
+  return upload_tree(ctx, tree);
+}
+
+int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
+  if (!ctx) return 1;
+  if (ctx->n_tgt == 0) {
+    ctx->tgt_ready = true;
+    return 0;
+  }
+  CU(cudaSetDevice(ctx->device));
+  std::vector<float> pts(ctx->n_tgt * 4);
+  CU(cudaMemcpyAsync(pts.data(), ctx->tgt_orig_pts.p, ctx->n_tgt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  FlatTree tree;
+  std::string err;
+  if (!build_flat_tree(pts.data(), ctx->n_tgt, max_leaf_size, tree, err)) return fail(ctx, 1, "sgb_target_build_kdtree: " + err);
+  return upload_tree(ctx, tree);
+}
+
+int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, const int32_t* coords, const double* means, const double* covs, int search_offsets) {
+  if (!ctx) return 1;
+  if (!(leaf_size > 0.0)) return fail(ctx, 1, "sgb_target_set_voxelmap: leaf_size must be positive");
+  if (search_offsets != 1 && search_offsets != 7 && search_offsets != 27) search_offsets = 1;  // incremental_voxelmap.hpp:159-163
+  if (n_voxels && (!coords || !means)) return fail(ctx, 1, "sgb_target_set_voxelmap: null input");
+  if (n_voxels >= (1ull << 30)) return fail(ctx, 1, "sgb_target_set_voxelmap: too many voxels");
+  CU(cudaSetDevice(ctx->device));
+  ctx->n_tgt = n_voxels;
+  ctx->tgt_has_normals = false;
+  ctx->tgt_has_covs = covs != nullptr;
+  ctx->tgt_is_voxel = true;
+  ctx->tgt_ready = true;
+  ctx->have_lin = false;
+  ctx->vox_offsets = search_offsets;
+  ctx->vox_inv_leaf = 1.0 / leaf_size;
+  CU(ctx->tgt_centre.reserve(4 * sizeof(double)));
+  CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
+  if (n_voxels == 0) return 0;
+  const size_t n = n_voxels;
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, means, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (covs) {
+    CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
+  }
+  CU(ctx->tgt_pts.reserve(n * sizeof(float4)));
+  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->tgt_bounds.as<double>(), ctx->tgt_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, covs ? ctx->stage_covs.as<double>() : nullptr, n, ctx->tgt_centre.as<double>(),
+                    ctx->tgt_pts.as<float4>(), nullptr, ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->sm_count, ctx->stream));
+  ctx->launches += 4;
+  // open-addressing table (x, y, z, voxel id), load factor <= 0.5, built on the host
+  size_t capacity = 16;
+  while (capacity < 2 * n) capacity <<= 1;
+  std::vector<int32_t> table(capacity * 4, -1);
+  const uint32_t mask = static_cast<uint32_t>(capacity - 1);
+  for (size_t i = 0; i < n; i++) {
+    const int x = coords[i * 3 + 0], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
+    uint32_t slot = host_vox_hash(x, y, z) & mask;
+    while (table[slot * 4 + 3] >= 0) {
+      if (table[slot * 4 + 0] == x && table[slot * 4 + 1] == y && table[slot * 4 + 2] == z) return fail(ctx, 1, "sgb_target_set_voxelmap: duplicate voxel coordinate");
+      slot = (slot + 1) & mask;
+    }
+    table[slot * 4 + 0] = x;
+    table[slot * 4 + 1] = y;
+    table[slot * 4 + 2] = z;
+    table[slot * 4 + 3] = static_cast<int32_t>(i);
+  }
+  CU(ctx->vox_table.reserve(capacity * sizeof(int4)));
+  CU(cudaMemcpyAsync(ctx->vox_table.p, table.data(), capacity * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->vox_mask = mask;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const double* covs) {
+  if (!ctx) return 1;
+  if (n && !points) return fail(ctx, 1, "sgb_source_set_points: null points");
+  if (n >= (1ull << 31)) return fail(ctx, 1, "sgb_source_set_points: too many points");
+  CU(cudaSetDevice(ctx->device));
+  ctx->n_src = n;
+  ctx->src_has_covs = covs != nullptr;
+  ctx->have_lin = false;
+  CU(ctx->src_centre.reserve(4 * sizeof(double)));
+  CU(ctx->src_bounds.reserve(6 * sizeof(double)));
+  if (n == 0) return 0;
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (covs) {
+    CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
+    CU(ctx->src_covA.reserve(n * sizeof(float4)));
+    CU(ctx->src_covB.reserve(n * sizeof(float4)));
+  }
+  CU(ctx->tmp_pts.reserve(n * sizeof(float4)));
+  CU(ctx->src_pts.reserve(n * sizeof(float4)));
+  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
+  CU(ctx->src_perm.reserve(n * sizeof(uint32_t)));
+  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->src_bounds.as<double>(), ctx->src_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, covs ? ctx->stage_covs.as<double>() : nullptr, n, ctx->src_centre.as<double>(),
+                    ctx->tmp_pts.as<float4>(), nullptr, ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), ctx->keys_in.as<uint64_t>(),
+                    ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  // Morton order: consecutive lanes get spatially adjacent queries (coherent tree paths, coalesced gathers)
+  size_t temp_bytes = 0;
+  CU(sort_pairs_u64_u32(nullptr, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->src_perm.as<uint32_t>(), n, ctx->stream));
+  CU(ctx->sort_temp.reserve(temp_bytes));
+  CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->src_perm.as<uint32_t>(), n, ctx->stream));
+  CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_pts.as<float4>(), ctx->src_pts.as<float4>(), covs ? ctx->tmp_covA.as<float4>() : nullptr,
+                   ctx->src_covA.as<float4>(), covs ? ctx->tmp_covB.as<float4>() : nullptr, ctx->src_covB.as<float4>(), nullptr, nullptr, ctx->sm_count,
+                   ctx->stream));
+  ctx->launches += 5;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int sgb_linearize_device(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* d_out44) {
+  if (!ctx) return 1;
+  if (!d_out44) return fail(ctx, 1, "sgb_linearize_device: null output");
+  return do_linearize(ctx, factor, robust, robust_c, rejector, max_dist_sq, T, d_out44);
+}
+
+int sgb_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* out_Hbe43) {
+  if (!ctx) return 1;
+  if (!out_Hbe43) return fail(ctx, 1, "sgb_linearize: null output");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->out44.reserve(64 * sizeof(double)));
+  if (int rc = do_linearize(ctx, factor, robust, robust_c, rejector, max_dist_sq, T, ctx->out44.as<double>())) return rc;
+  CU(cudaMemcpyAsync(ctx->h_out, ctx->out44.p, 44 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out_Hbe43, ctx->h_out, 43 * sizeof(double));
+  return 0;
+}
+
+int sgb_error_device(sgb_ctx* ctx, const double* T, double* d_out1) {
+  if (!ctx) return 1;
+  if (!d_out1) return fail(ctx, 1, "sgb_error_device: null output");
+  return do_error(ctx, T, d_out1);
+}
+
+int sgb_error(sgb_ctx* ctx, const double* T, double* out_e) {
+  if (!ctx) return 1;
+  if (!out_e) return fail(ctx, 1, "sgb_error: null output");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->out44.reserve(64 * sizeof(double)));
+  double* d_e = ctx->out44.as<double>() + 48;  // keep H|b|e|inliers of the last linearize intact
+  if (int rc = do_error(ctx, T, d_e)) return rc;
+  CU(cudaMemcpyAsync(ctx->h_out + 48, d_e, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out_e = ctx->h_out[48];
+  return 0;
+}
+
+int sgb_correspondences(sgb_ctx* ctx, uint64_t* target_index) {
+  if (!ctx) return 1;
+  if (!ctx->have_lin) return fail(ctx, 1, "sgb_correspondences: no preceding sgb_linearize");
+  if (ctx->n_src == 0) return 0;
+  if (!target_index) return fail(ctx, 1, "sgb_correspondences: null output");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->corr64.reserve(ctx->n_src * sizeof(uint64_t)));
+  CU(launch_correspondences(ctx->corr.as<uint32_t>(), ctx->src_perm.as<uint32_t>(), ctx->n_src, ctx->tgt_pts.as<float4>(), ctx->tgt_is_voxel ? 1 : 0,
+                            ctx->corr64.as<uint64_t>(), ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(target_index, ctx->corr64.p, ctx->n_src * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int sgb_num_inliers(sgb_ctx* ctx, size_t* n) {
+  if (!ctx || !n) return 1;
+  if (!ctx->have_lin || !ctx->last_out) return fail(ctx, 1, "sgb_num_inliers: no preceding sgb_linearize");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->h_out + 56, ctx->last_out + 43, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *n = static_cast<size_t>(ctx->h_out[56] + 0.5);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// SPDX-License-Identifier: MIT
+// Device-side data layout and per-point math of the B200 hot path.  See DESIGN.md §3-4.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgb {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;  // no correspondence
+constexpr int kLinBlock = 128;           // threads per CTA of the linearize / error kernels
+constexpr int kAcc = 28;                 // 6 (H_rr sym) + 9 (H_rt) + 6 (H_tt sym) + 6 (b) + 1 (e)
+constexpr int kPartialStride = 32;       // doubles per CTA partial (28 sums + inlier count, padded)
+
+/// Flattened kd-tree node, 8 bytes, nodes in PRE-ORDER so that the left child of node i is i+1.
+///   inner: x = split threshold (float bits), y = (right_child << 2) | axis        (axis in 0..2)
+///   leaf : x = first point (offset into the leaf-ordered point arrays), y = (count << 2) | 3
+using KdNode = uint2;
+
+struct DevTarget {
+  const float4* pts;      // leaf order; xyz relative to `centre`; w = original index (int bits) / unused for voxels
+  const float4* normals;  // leaf order (plane ICP) or null
+  const float4* covA;     // (xx, xy, xz, yy)
+  const float4* covB;     // (yz, zz, 0, 0)
+  const KdNode* nodes;    // kd-tree (null for voxel maps)
+  const double* centre;   // 3 doubles, device
+  // voxel map (VGICP)
+  const int4* vox_table;  // open addressing: (x, y, z, voxel_id), voxel_id < 0 = empty
+  uint32_t vox_mask;      // capacity - 1 (power of two)
+  int vox_num_offsets;    // 1, 7 or 27
+  double vox_inv_leaf;
+};
+
+struct DevSource {
+  const float4* pts;   // Morton order; xyz relative to `centre`
+  const float4* covA;  // Morton order
+  const float4* covB;
+  const double* centre;  // 3 doubles, device
+  uint32_t n;
+};
+
+struct LinParams {
+  DevTarget tgt;
+  DevSource src;
+  double T[12];      // row-major R (9) then t (3): T_target_source of this call
+  double Tlin[12];   // pose of the last linearize (error kernel, GICP precision matrix)
+  float max_dist_sq;  // seeded search bound (FLT_MAX for NullRejector)
+  double robust_c;
+  uint32_t* corr;     // per source point (Morton order): leaf-order position / voxel id, or kNone
+  double* partials;   // gridDim.x * kPartialStride
+  unsigned int* ticket;
+  double* out;        // 44 doubles: H(36) | b(6) | e | num_inliers     (error kernel: out[0] = e)
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vox_hash(int x, int y, int z) {
+  // any hash works (lookups are exact-match); this is a 32-bit mix of the three coordinates
+  uint32_t h = static_cast<uint32_t>(x) * 73856093u ^ static_cast<uint32_t>(y) * 19349669u ^ static_cast<uint32_t>(z) * 83492791u;
+  h ^= h >> 15;
+  h *= 0x2c1b3c6du;
+  h ^= h >> 12;
+  return h;
+}
+
+/// Symmetric 3x3 stored as (xx, xy, xz, yy, yz, zz).
+struct Sym3 {
+  double xx, xy, xz, yy, yz, zz;
+};
+
+__device__ __forceinline__ Sym3 sym3_inverse(const Sym3& a) {
+  // cofactors / determinant (the closed form Eigen uses for 3x3, gicp_factor.hpp:60)
+  const double c00 = a.yy * a.zz - a.yz * a.yz;
+  const double c01 = a.xz * a.yz - a.xy * a.zz;
+  const double c02 = a.xy * a.yz - a.xz * a.yy;
+  const double c11 = a.xx * a.zz - a.xz * a.xz;
+  const double c12 = a.xy * a.xz - a.xx * a.yz;
+  const double c22 = a.xx * a.yy - a.xy * a.xy;
+  const double det = a.xx * c00 + a.xy * c01 + a.xz * c02;
+  const double inv = 1.0 / det;
+  return Sym3{c00 * inv, c01 * inv, c02 * inv, c11 * inv, c12 * inv, c22 * inv};
+}
+
+/// RCR = Ct + R Cs R^T (3x3 blocks of gicp_factor.hpp:59) ; returns its inverse (the fused precision matrix).
+__device__ __forceinline__ Sym3 gicp_precision(const double* R, const float4& sA, const float4& sB, const float4& tA, const float4& tB) {
+  const double sxx = sA.x, sxy = sA.y, sxz = sA.z, syy = sA.w, syz = sB.x, szz = sB.y;
+  // A = R * Cs
+  double A[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double r0 = R[i * 3 + 0], r1 = R[i * 3 + 1], r2 = R[i * 3 + 2];
+    A[i * 3 + 0] = r0 * sxx + r1 * sxy + r2 * sxz;
+    A[i * 3 + 1] = r0 * sxy + r1 * syy + r2 * syz;
+    A[i * 3 + 2] = r0 * sxz + r1 * syz + r2 * szz;
+  }
+  Sym3 rcr;
+  rcr.xx = static_cast<double>(tA.x) + (A[0] * R[0] + A[1] * R[1] + A[2] * R[2]);
+  rcr.xy = static_cast<double>(tA.y) + (A[0] * R[3] + A[1] * R[4] + A[2] * R[5]);
+  rcr.xz = static_cast<double>(tA.z) + (A[0] * R[6] + A[1] * R[7] + A[2] * R[8]);
+  rcr.yy = static_cast<double>(tA.w) + (A[3] * R[3] + A[4] * R[4] + A[5] * R[5]);
+  rcr.yz = static_cast<double>(tB.x) + (A[3] * R[6] + A[4] * R[7] + A[5] * R[8]);
+  rcr.zz = static_cast<double>(tB.y) + (A[6] * R[6] + A[7] * R[7] + A[8] * R[8]);
+  return sym3_inverse(rcr);
+}
+
+/// Accumulate one point's  J^T M J | J^T M r | 1/2 r^T M r  (scaled by w) into acc[28], where
+/// J = [R skew(p) | -R]  (icp_factor.hpp:45-47) and M is the 3x3 weight in the target frame:
+/// identity (ICP), diag(n.^2) (point-to-plane, plane_icp_factor.hpp:46-55) or (Ct + R Cs R^T)^-1 (GICP).
+/// Returns the unweighted error e.
+template <int ROBUST>
+__device__ __forceinline__ void accumulate_factor(const double* R, const Sym3& M, double rx, double ry, double rz, double px, double py, double pz,
+                                                  double robust_c, double* acc) {
+  // Mr, e
+  const double mrx = M.xx * rx + M.xy * ry + M.xz * rz;
+  const double mry = M.xy * rx + M.yy * ry + M.yz * rz;
+  const double mrz = M.xz * rx + M.yz * ry + M.zz * rz;
+  const double e = 0.5 * (rx * mrx + ry * mry + rz * mrz);
+  double w = 1.0;
+  if (ROBUST == 1) {  // Huber, robust_kernel.hpp:24-27 on sqrt(e) (robust_kernel.hpp:84)
+    const double x = sqrt(e);
+    w = x < robust_c ? 1.0 : robust_c / x;
+  } else if (ROBUST == 2) {  // Cauchy, robust_kernel.hpp:47 : c / (c + x^2) with x = sqrt(e)
+    const double x = sqrt(e);
+    w = robust_c / (robust_c + x * x);
+  }
+  // MR = M * R ; D = R^T * MR (symmetric)
+  double MR[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double r0 = R[0 + j], r1 = R[3 + j], r2 = R[6 + j];
+    MR[0 + j] = M.xx * r0 + M.xy * r1 + M.xz * r2;
+    MR[3 + j] = M.xy * r0 + M.yy * r1 + M.yz * r2;
+    MR[6 + j] = M.xz * r0 + M.yz * r1 + M.zz * r2;
+  }
+  const double d00 = w * (R[0] * MR[0] + R[3] * MR[3] + R[6] * MR[6]);
+  const double d01 = w * (R[0] * MR[1] + R[3] * MR[4] + R[6] * MR[7]);
+  const double d02 = w * (R[0] * MR[2] + R[3] * MR[5] + R[6] * MR[8]);
+  const double d11 = w * (R[1] * MR[1] + R[4] * MR[4] + R[7] * MR[7]);
+  const double d12 = w * (R[1] * MR[2] + R[4] * MR[5] + R[7] * MR[8]);
+  const double d22 = w * (R[2] * MR[2] + R[5] * MR[5] + R[8] * MR[8]);
+  // g = w * R^T (M r)
+  const double gx = w * (R[0] * mrx + R[3] * mry + R[6] * mrz);
+  const double gy = w * (R[1] * mrx + R[4] * mry + R[7] * mrz);
+  const double gz = w * (R[2] * mrx + R[5] * mry + R[8] * mrz);
+  // U = skew(p) * D : column j = p x D[:, j]      (H_rt = U)
+  const double u00 = py * d02 - pz * d01, u01 = py * d12 - pz * d11, u02 = py * d22 - pz * d12;
+  const double u10 = pz * d00 - px * d02, u11 = pz * d01 - px * d12, u12 = pz * d02 - px * d22;
+  const double u20 = px * d01 - py * d00, u21 = px * d11 - py * d01, u22 = px * d12 - py * d02;
+  // H_rr = skew(p)^T D skew(p) : row i = p x U[i, :]
+  acc[0] += py * u02 - pz * u01;
+  acc[1] += pz * u00 - px * u02;
+  acc[2] += px * u01 - py * u00;
+  acc[3] += pz * u10 - px * u12;
+  acc[4] += px * u11 - py * u10;
+  acc[5] += px * u21 - py * u20;
+  acc[6] += u00;
+  acc[7] += u01;
+  acc[8] += u02;
+  acc[9] += u10;
+  acc[10] += u11;
+  acc[11] += u12;
+  acc[12] += u20;
+  acc[13] += u21;
+  acc[14] += u22;
+  acc[15] += d00;
+  acc[16] += d01;
+  acc[17] += d02;
+  acc[18] += d11;
+  acc[19] += d12;
+  acc[20] += d22;
+  // b = J^T M r = [ g x p ; -g ]
+  acc[21] += gy * pz - gz * py;
+  acc[22] += gz * px - gx * pz;
+  acc[23] += gx * py - gy * px;
+  acc[24] -= gx;
+  acc[25] -= gy;
+  acc[26] -= gz;
+  acc[27] += w * e;
+}
+
+/// Exact nearest neighbour of q in the flattened kd-tree (restates the visiting order of
+/// UnsafeKdTree::knn_search, ann/kdtree.hpp:193-233, with an explicit stack of far children).
+/// `best_d` enters as the search bound (only strictly closer points are accepted, knn_result.hpp:81-83).
+/// stack: shared memory, entry (s, lane) at stack[s * kLinBlock + threadIdx.x].
+__device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, float qx, float qy, float qz,
+                                               float& best_d, uint2* stack) {
+  uint32_t best = kNone;
+  uint32_t node = 0;
+  int sp = 0;
+  uint2* my_stack = stack + threadIdx.x;
+  for (;;) {
+    KdNode nd = __ldg(&nodes[node]);
+    uint32_t kind = nd.y & 3u;
+    while (kind != 3u) {  // descend, remembering the far child and its plane distance
+      const float qv = kind == 0u ? qx : (kind == 1u ? qy : qz);
+      const float diff = qv - __uint_as_float(nd.x);
+      const uint32_t right = nd.y >> 2, left = node + 1u;
+      const bool go_left = diff < 0.0f;
+      my_stack[sp * kLinBlock] = make_uint2(go_left ? right : left, __float_as_uint(diff * diff));
+      sp++;
+      node = go_left ? left : right;
+      nd = __ldg(&nodes[node]);
+      kind = nd.y & 3u;
+    }
+    {  // leaf: scan its contiguous block of points
+      const uint32_t first = nd.x, cnt = nd.y >> 2;
+      const float4* lp = pts + first;
+#pragma unroll 4
+      for (uint32_t j = 0; j < cnt; j++) {
+        const float4 t = __ldg(&lp[j]);
+        const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best_d) {
+          best_d = d;
+          best = first + j;
+        }
+      }
+    }
+    // backtrack: nearest pending far child whose splitting plane is closer than the best distance
+    bool found = false;
+    while (sp > 0) {
+      sp--;
+      const uint2 e = my_stack[sp * kLinBlock];
+      if (__uint_as_float(e.y) < best_d) {
+        node = e.x;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+  return best;
+}
+
+/// Block-wide sum of per-thread accumulators -> partials[blockIdx.x]; the last CTA to finish adds all
+/// partials in CTA order (deterministic) and writes the expanded 44-double result.
+template <int NACC, bool EXPAND>
+__device__ __forceinline__ void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out) {
+  __shared__ double s_red[kLinBlock / 32][NACC];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinBlock / 32; w++) v += s_red[w][threadIdx.x];
+    partials[static_cast<size_t>(blockIdx.x) * kPartialStride + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < NACC) {
+    double v = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++) v += __ldcg(&partials[static_cast<size_t>(b) * kPartialStride + threadIdx.x]);
+    if (!EXPAND) {
+      out[threadIdx.x] = v;
+    } else {
+      // acc index -> positions in H(6x6 row-major) | b | e | inliers
+      const int k = threadIdx.x;
+      if (k < 6) {  // H_rr upper triangle: (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+        const int r = k < 3 ? 0 : (k < 5 ? 1 : 2);
+        const int c = k < 3 ? k : (k < 5 ? k - 2 : 2);
+        out[r * 6 + c] = v;
+        out[c * 6 + r] = v;
+      } else if (k < 15) {  // H_rt 3x3 row-major -> rows 0..2, cols 3..5 (+ transpose)
+        const int r = (k - 6) / 3, c = (k - 6) % 3;
+        out[r * 6 + 3 + c] = v;
+        out[(3 + c) * 6 + r] = v;
+      } else if (k < 21) {  // H_tt upper triangle
+        const int kk = k - 15;
+        const int r = kk < 3 ? 0 : (kk < 5 ? 1 : 2);
+        const int c = kk < 3 ? kk : (kk < 5 ? kk - 2 : 2);
+        out[(3 + r) * 6 + 3 + c] = v;
+        out[(3 + c) * 6 + 3 + r] = v;
+      } else if (k < 27) {
+        out[36 + (k - 21)] = v;
+      } else if (k == 27) {
+        out[42] = v;
+      } else {
+        out[43] = v;  // inlier count
+      }
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
+}
+
+}  // namespace sgb

@@ -1,0 +1,413 @@
+// SPDX-License-Identifier: MIT
+// Hot-path kernels (sm_100a): fused transform -> kd-tree NN -> reject -> factor -> reduction, the
+// error() kernel for the LM inner loop, and the one-off layout kernels (upload conversion, Morton
+// ordering of the source, leaf ordering of the target).  See DESIGN.md §4 for the roofline of each.
+#include "sgb_device.cuh"
+#include "sgb_kernels.h"
+
+#include <cfloat>
+#include <cub/device/device_radix_sort.cuh>
+
+namespace sgb {
+
+// =============================================================================================
+// linearize: one thread per source point (grid-stride, Morton-ordered so a warp's queries share
+// their path through the tree), FP32 search on FP32 coordinates, FP64 factor algebra and sums.
+// =============================================================================================
+template <int FACTOR, int ROBUST>
+__global__ void __launch_bounds__(kLinBlock) linearize_kd_kernel(const __grid_constant__ LinParams P) {
+  extern __shared__ uint2 s_stack[];
+  double acc[kAcc + 1];
+#pragma unroll
+  for (int k = 0; k <= kAcc; k++) acc[k] = 0.0;
+
+  // pose in the centred frames:  p' - c_t = R p_f + (R c_s + t - c_t)
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
+
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
+    const float4 sp = __ldg(&P.src.pts[i]);
+    const double sx = sp.x, sy = sp.y, sz = sp.z;
+    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
+    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
+    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+
+    float best_d = P.max_dist_sq;
+    const uint32_t best = kd_nearest(P.tgt.nodes, P.tgt.pts, static_cast<float>(qx), static_cast<float>(qy), static_cast<float>(qz), best_d, s_stack);
+    P.corr[i] = best;
+    if (best == kNone) continue;
+
+    const float4 tq = __ldg(&P.tgt.pts[best]);
+    const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
+    Sym3 M;
+    if (FACTOR == 0) {
+      M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+    } else if (FACTOR == 1) {
+      const float4 n = __ldg(&P.tgt.normals[best]);
+      M = Sym3{static_cast<double>(n.x) * n.x, 0.0, 0.0, static_cast<double>(n.y) * n.y, 0.0, static_cast<double>(n.z) * n.z};
+    } else {
+      M = gicp_precision(R, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[best]), __ldg(&P.tgt.covB[best]));
+    }
+    accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
+    acc[kAcc] += 1.0;
+  }
+  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
+}
+
+// Gaussian-voxel-map target (VGICP): hash probe of 1 / 7 / 27 voxels in the reference's offset order
+// (incremental_voxelmap.hpp:157-186), nearest voxel mean wins, first-found wins ties (knn_result.hpp:81-83).
+__device__ __forceinline__ void vox_offset(int num, int o, int& dx, int& dy, int& dz) {
+  if (num == 27) {  // for i, j, k in -1..1 (lexicographic)
+    dx = o / 9 - 1;
+    dy = (o / 3) % 3 - 1;
+    dz = o % 3 - 1;
+  } else {  // 1 or 7: centre, +x, +y, +z, -x, -y, -z
+    const int s = o == 0 ? 0 : (o <= 3 ? 1 : -1);
+    const int a = o == 0 ? -1 : (o - 1) % 3;
+    dx = a == 0 ? s : 0;
+    dy = a == 1 ? s : 0;
+    dz = a == 2 ? s : 0;
+  }
+}
+
+template <int FACTOR, int ROBUST>
+__global__ void __launch_bounds__(kLinBlock) linearize_vox_kernel(const __grid_constant__ LinParams P) {
+  double acc[kAcc + 1];
+#pragma unroll
+  for (int k = 0; k <= kAcc; k++) acc[k] = 0.0;
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double ctx = P.tgt.centre[0], cty = P.tgt.centre[1], ctz = P.tgt.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - ctx;
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - cty;
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - ctz;
+  const double max_d = P.max_dist_sq >= FLT_MAX ? DBL_MAX : static_cast<double>(P.max_dist_sq);
+
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
+    const float4 sp = __ldg(&P.src.pts[i]);
+    const double sx = sp.x, sy = sp.y, sz = sp.z;
+    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
+    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
+    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+    // voxel coordinate of the un-centred point, fast_floor semantics == floor (util/fast_floor.hpp:12-15)
+    const int cx = static_cast<int>(floor((qx + ctx) * P.tgt.vox_inv_leaf));
+    const int cy = static_cast<int>(floor((qy + cty) * P.tgt.vox_inv_leaf));
+    const int cz = static_cast<int>(floor((qz + ctz) * P.tgt.vox_inv_leaf));
+    double best_d = DBL_MAX;
+    uint32_t best = kNone;
+    double brx = 0, bry = 0, brz = 0;
+    for (int o = 0; o < P.tgt.vox_num_offsets; o++) {
+      int ox, oy, oz;
+      vox_offset(P.tgt.vox_num_offsets, o, ox, oy, oz);
+      const int vx = cx + ox, vy = cy + oy, vz = cz + oz;
+      uint32_t slot = vox_hash(vx, vy, vz) & P.tgt.vox_mask;
+      for (;;) {
+        const int4 e = __ldg(&P.tgt.vox_table[slot]);
+        if (e.w < 0) break;
+        if (e.x == vx && e.y == vy && e.z == vz) {
+          const float4 m = __ldg(&P.tgt.pts[e.w]);
+          const double dx = static_cast<double>(m.x) - qx, dy = static_cast<double>(m.y) - qy, dz = static_cast<double>(m.z) - qz;
+          const double d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = static_cast<uint32_t>(e.w);
+            brx = dx;
+            bry = dy;
+            brz = dz;
+          }
+          break;
+        }
+        slot = (slot + 1u) & P.tgt.vox_mask;
+      }
+    }
+    if (best != kNone && best_d > max_d) best = kNone;  // DistanceRejector, rejector.hpp:23-25
+    P.corr[i] = best;
+    if (best == kNone) continue;
+    Sym3 M;
+    if (FACTOR == 2) {
+      M = gicp_precision(R, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[best]), __ldg(&P.tgt.covB[best]));
+    } else {
+      M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+    }
+    accumulate_factor<ROBUST>(R, M, brx, bry, brz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
+    acc[kAcc] += 1.0;
+  }
+  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
+}
+
+// =============================================================================================
+// error(): cached correspondences, trial pose T, GICP precision matrix re-derived from the pose of
+// the last linearize (gicp_factor.hpp:81-89).  Pure streaming + gather.
+// =============================================================================================
+template <int FACTOR, int ROBUST>
+__global__ void __launch_bounds__(kLinBlock) error_kernel(const __grid_constant__ LinParams P) {
+  double acc[1] = {0.0};
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
+    const uint32_t k = __ldg(&P.corr[i]);
+    if (k == kNone) continue;
+    const float4 sp = __ldg(&P.src.pts[i]);
+    const double sx = sp.x, sy = sp.y, sz = sp.z;
+    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
+    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
+    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+    const float4 tq = __ldg(&P.tgt.pts[k]);
+    const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
+    double e;
+    if (FACTOR == 0) {
+      e = 0.5 * (rx * rx + ry * ry + rz * rz);
+    } else if (FACTOR == 1) {
+      const float4 n = __ldg(&P.tgt.normals[k]);
+      const double ex = static_cast<double>(n.x) * rx, ey = static_cast<double>(n.y) * ry, ez = static_cast<double>(n.z) * rz;
+      e = 0.5 * (ex * ex + ey * ey + ez * ez);
+    } else {
+      const Sym3 M = gicp_precision(P.Tlin, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[k]), __ldg(&P.tgt.covB[k]));
+      const double mrx = M.xx * rx + M.xy * ry + M.xz * rz;
+      const double mry = M.xy * rx + M.yy * ry + M.yz * rz;
+      const double mrz = M.xz * rx + M.yz * ry + M.zz * rz;
+      e = 0.5 * (rx * mrx + ry * mry + rz * mrz);
+    }
+    if (ROBUST == 1) {
+      const double x = sqrt(e);
+      e *= (x < P.robust_c ? 1.0 : P.robust_c / x);
+    } else if (ROBUST == 2) {
+      const double x = sqrt(e);
+      e *= P.robust_c / (P.robust_c + x * x);
+    }
+    acc[0] += e;
+  }
+  block_reduce_and_finish<1, false>(acc, P.partials, P.ticket, P.out);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int FACTOR, int ROBUST>
+static cudaError_t launch_lin(const LinParams& P, bool voxel, int grid, size_t smem, cudaStream_t st) {
+  if (voxel) {
+    if (FACTOR == 1) return cudaErrorInvalidValue;
+    linearize_vox_kernel<(FACTOR == 1 ? 0 : FACTOR), ROBUST><<<grid, kLinBlock, 0, st>>>(P);
+  } else {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(linearize_kd_kernel<FACTOR, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    linearize_kd_kernel<FACTOR, ROBUST><<<grid, kLinBlock, smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+template <int FACTOR, int ROBUST>
+static cudaError_t launch_err(const LinParams& P, int grid, cudaStream_t st) {
+  error_kernel<FACTOR, ROBUST><<<grid, kLinBlock, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
+#define SGB_DISPATCH(FN, ...)                                      \
+  switch (factor * 3 + robust) {                                   \
+    case 0: return FN<0, 0>(__VA_ARGS__);                          \
+    case 1: return FN<0, 1>(__VA_ARGS__);                          \
+    case 2: return FN<0, 2>(__VA_ARGS__);                          \
+    case 3: return FN<1, 0>(__VA_ARGS__);                          \
+    case 4: return FN<1, 1>(__VA_ARGS__);                          \
+    case 5: return FN<1, 2>(__VA_ARGS__);                          \
+    case 6: return FN<2, 0>(__VA_ARGS__);                          \
+    case 7: return FN<2, 1>(__VA_ARGS__);                          \
+    case 8: return FN<2, 2>(__VA_ARGS__);                          \
+    default: return cudaErrorInvalidValue;                         \
+  }
+
+cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool voxel, int grid, int stack_depth, cudaStream_t st) {
+  const size_t smem = voxel ? 0 : static_cast<size_t>(stack_depth) * kLinBlock * sizeof(uint2);
+  SGB_DISPATCH(launch_lin, P, voxel, grid, smem, st);
+}
+cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st) { SGB_DISPATCH(launch_err, P, grid, st); }
+
+int linearize_occupancy(int stack_depth) {
+  int nb = 0;
+  const size_t smem = static_cast<size_t>(stack_depth) * kLinBlock * sizeof(uint2);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(linearize_kd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, linearize_kd_kernel<2, 0>, kLinBlock, smem) != cudaSuccess) return 1;
+  return nb > 0 ? nb : 1;
+}
+
+// =============================================================================================
+// One-off layout kernels
+// =============================================================================================
+// min/max of N x 4 doubles (xyz used) -> bounds[6] via ordered-int atomics on doubles
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) <= v) break;
+    old = atomicCAS(a, assumed, static_cast<unsigned long long>(__double_as_longlong(v)));
+  } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) >= v) break;
+    old = atomicCAS(a, assumed, static_cast<unsigned long long>(__double_as_longlong(v)));
+  } while (assumed != old);
+}
+
+__global__ void bounds_init_kernel(double* bounds) {
+  if (threadIdx.x < 3) bounds[threadIdx.x] = DBL_MAX;
+  if (threadIdx.x >= 3 && threadIdx.x < 6) bounds[threadIdx.x] = -DBL_MAX;
+}
+
+__global__ void bounds_kernel(const double4* __restrict__ pts, size_t n, double* bounds) {
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double4 p = pts[i];
+    lo[0] = fmin(lo[0], p.x); lo[1] = fmin(lo[1], p.y); lo[2] = fmin(lo[2], p.z);
+    hi[0] = fmax(hi[0], p.x); hi[1] = fmax(hi[1], p.y); hi[2] = fmax(hi[2], p.z);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_down_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_down_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      atomic_min_double(&bounds[d], lo[d]);
+      atomic_max_double(&bounds[3 + d], hi[d]);
+    }
+  }
+}
+
+// centre = box centre ; also emit the Morton scale
+__global__ void centre_kernel(const double* bounds, double* centre) {
+  if (threadIdx.x < 3) {
+    const double lo = bounds[threadIdx.x], hi = bounds[3 + threadIdx.x];
+    centre[threadIdx.x] = (lo <= hi) ? 0.5 * (lo + hi) : 0.0;
+  }
+  if (threadIdx.x == 3) {
+    double ext = 0.0;
+    for (int d = 0; d < 3; d++) ext = fmax(ext, bounds[3 + d] - bounds[d]);
+    centre[3] = ext > 0.0 ? ext : 1.0;  // largest extent
+  }
+}
+
+__device__ __forceinline__ float4 pack_covA(const double* c) { return make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[5]); }
+__device__ __forceinline__ float4 pack_covB(const double* c) { return make_float4((float)c[6], (float)c[10], 0.f, 0.f); }
+
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {  // 21 bits -> every third bit
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+// raw (double AoS) -> centred float4 in ORIGINAL order (w = index), optional features, optional Morton key
+__global__ void convert_kernel(const double4* __restrict__ pts, const double4* __restrict__ normals, const double* __restrict__ covs, size_t n,
+                               const double* __restrict__ centre, float4* out_pts, float4* out_normals, float4* out_covA, float4* out_covB,
+                               uint64_t* keys, uint32_t* vals) {
+  const double cx = centre[0], cy = centre[1], cz = centre[2];
+  const double inv_ext = 2097151.0 / centre[3];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double4 p = pts[i];
+    const double x = p.x - cx, y = p.y - cy, z = p.z - cz;
+    out_pts[i] = make_float4((float)x, (float)y, (float)z, __int_as_float(static_cast<int>(i)));
+    if (normals) {
+      const double4 nn = normals[i];
+      out_normals[i] = make_float4((float)nn.x, (float)nn.y, (float)nn.z, 0.f);
+    }
+    if (covs) {
+      const double* c = covs + i * 16;
+      out_covA[i] = pack_covA(c);
+      out_covB[i] = pack_covB(c);
+    }
+    if (keys) {
+      const double h = 0.5 * centre[3];
+      const uint64_t kx = static_cast<uint64_t>(fmin(fmax((x + h) * inv_ext, 0.0), 2097151.0));
+      const uint64_t ky = static_cast<uint64_t>(fmin(fmax((y + h) * inv_ext, 0.0), 2097151.0));
+      const uint64_t kz = static_cast<uint64_t>(fmin(fmax((z + h) * inv_ext, 0.0), 2097151.0));
+      keys[i] = spread21(kx) | (spread21(ky) << 1) | (spread21(kz) << 2);
+      vals[i] = static_cast<uint32_t>(i);
+    }
+  }
+}
+
+// out[j] = in[perm[j]] for up to four float4 streams (leaf ordering of the target / Morton ordering of the source)
+__global__ void gather_kernel(const uint32_t* __restrict__ perm, size_t n, const float4* __restrict__ in0, float4* out0, const float4* __restrict__ in1,
+                              float4* out1, const float4* __restrict__ in2, float4* out2, const float4* __restrict__ in3, float4* out3) {
+  for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < n; j += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t s = perm[j];
+    if (in0) out0[j] = in0[s];
+    if (in1) out1[j] = in1[s];
+    if (in2) out2[j] = in2[s];
+    if (in3) out3[j] = in3[s];
+  }
+}
+
+// correspondences in the caller's order: out[perm[i]] = original target index (or voxel id << 32)
+__global__ void correspondences_kernel(const uint32_t* __restrict__ corr, const uint32_t* __restrict__ perm, size_t n, const float4* __restrict__ tgt_pts,
+                                       int voxel, uint64_t* out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t k = corr[i];
+    uint64_t v = ~0ull;
+    if (k != kNone) v = voxel ? (static_cast<uint64_t>(k) << 32) : static_cast<uint64_t>(static_cast<uint32_t>(__float_as_int(tgt_pts[k].w)));
+    out[perm[i]] = v;
+  }
+}
+
+static int grid_for(size_t n, int block, int cap) {
+  size_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  return static_cast<int>(g);
+}
+
+cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bounds6, double* d_centre4, int sm_count, cudaStream_t st) {
+  bounds_init_kernel<<<1, 32, 0, st>>>(d_bounds6);
+  if (n) bounds_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(reinterpret_cast<const double4*>(d_pts4), n, d_bounds6);
+  centre_kernel<<<1, 32, 0, st>>>(d_bounds6, d_centre4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,
+                           float4* out_normals, float4* out_covA, float4* out_covB, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  convert_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(reinterpret_cast<const double4*>(d_pts4), reinterpret_cast<const double4*>(d_normals4), d_covs16,
+                                                                 n, d_centre4, out_pts, out_normals, out_covA, out_covB, keys, vals);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const uint32_t* perm, size_t n, const float4* in0, float4* out0, const float4* in1, float4* out1, const float4* in2, float4* out2,
+                          const float4* in3, float4* out3, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  gather_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(perm, n, in0, out0, in1, out1, in2, out2, in3, out3);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_correspondences(const uint32_t* corr, const uint32_t* perm, size_t n, const float4* tgt_pts, int voxel, uint64_t* out, int sm_count,
+                                   cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  correspondences_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(corr, perm, n, tgt_pts, voxel, out);
+  return cudaGetLastError();
+}
+
+cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                               size_t n, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0, 63, st);
+}
+
+}  // namespace sgb

@@ -1,0 +1,25 @@
+// SPDX-License-Identifier: MIT
+// Host-visible launchers of the kernels in sgb_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sgb_device.cuh"
+
+namespace sgb {
+
+cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool voxel, int grid, int stack_depth, cudaStream_t st);
+cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
+int linearize_occupancy(int stack_depth);
+
+cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bounds6, double* d_centre4, int sm_count, cudaStream_t st);
+cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,
+                           float4* out_normals, float4* out_covA, float4* out_covB, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);
+cudaError_t launch_gather(const uint32_t* perm, size_t n, const float4* in0, float4* out0, const float4* in1, float4* out1, const float4* in2, float4* out2,
+                          const float4* in3, float4* out3, int sm_count, cudaStream_t st);
+cudaError_t launch_correspondences(const uint32_t* corr, const uint32_t* perm, size_t n, const float4* tgt_pts, int voxel, uint64_t* out, int sm_count,
+                                   cudaStream_t st);
+cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                               size_t n, cudaStream_t st);
+
+}  // namespace sgb

@@ -1,0 +1,317 @@
+"""GPU parity: the CUDA hot path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Tolerances (FP32 coordinate/covariance storage, FP32 search, FP64 factor algebra and sums):
+  H      : ||H_gpu - H_cpu||_F <= 2e-5 ||H_cpu||_F
+  e      : |e_gpu - e_cpu| <= 2e-5 e_cpu
+  b      : |b_gpu - b_cpu|_k <= 2e-5 sqrt(2 e H_kk)           (Cauchy-Schwarz scale of b_k)
+  step   : |H^-1 b|_gpu - |H^-1 b|_cpu  <= 2e-6 (rad / m)
+  pose   : converged SE(3) within 1e-4 rad / 1e-3 m of the oracle (BASELINE.json north_star)
+  index  : identical correspondences except FP32 near-ties, where the two candidates' squared distances
+           must agree to 1e-5 relative (+1e-7 absolute)
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import noise_poses, pose_error
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5
+
+
+def _sg():
+    import small_gicp_b200 as sg
+
+    return sg
+
+
+def load_ctx(target, tree, source, own_tree=False):
+    sg = _sg()
+    ctx = sg.Context(0)
+    ctx.set_target(target.points, target.normals, target.covs)
+    if own_tree:
+        ctx.build_target_kdtree(0)
+    else:
+        nodes, idx = tree.export()
+        ctx.set_target_kdtree(nodes, idx)
+    ctx.set_source(source.points, source.covs)
+    return ctx
+
+
+def check_linearized(gpu, cpu, tag=""):
+    (H, b, e), (H0, b0, e0) = gpu, cpu
+    assert np.linalg.norm(H - H0) <= RTOL * np.linalg.norm(H0), (tag, np.linalg.norm(H - H0) / np.linalg.norm(H0))
+    np.testing.assert_allclose(H, H.T, atol=0)  # the kernel writes both triangles from one sum
+    assert abs(e - e0) <= RTOL * e0, (tag, e, e0)
+    scale = np.sqrt(2.0 * e0 * np.diag(H0))
+    assert np.all(np.abs(b - b0) <= RTOL * scale), (tag, np.abs(b - b0) / scale)
+    d, d0 = np.linalg.solve(H + 1e-6 * np.eye(6), -b), np.linalg.solve(H0 + 1e-6 * np.eye(6), -b0)
+    assert np.abs(d - d0).max() <= 2e-6, (tag, np.abs(d - d0).max())
+
+
+def check_correspondences(ctx, reg, target_pts, source_pts, T, max_mismatch=2e-3):
+    g = ctx.correspondences()
+    c = reg.correspondences(len(source_pts))
+    mism = np.nonzero(g != c)[0]
+    assert len(mism) <= max(2, max_mismatch * len(c)), (len(mism), len(c))
+    q = (source_pts @ T.T)[:, :3]
+    for i in mism:
+        dg = np.inf if g[i] == O.NO_INDEX else ((target_pts[int(g[i]), :3] - q[i]) ** 2).sum()
+        dc = np.inf if c[i] == O.NO_INDEX else ((target_pts[int(c[i]), :3] - q[i]) ** 2).sum()
+        if np.isinf(dg) or np.isinf(dc):  # rejector boundary: the other distance must sit at max_dist_sq
+            fin = dc if np.isinf(dg) else dg
+            assert abs(fin - 1.0) < 1e-4, (i, dg, dc)
+        else:
+            assert abs(dg - dc) <= 1e-5 * dc + 1e-7, (i, dg, dc)
+    return len(mism)
+
+
+FACTORS = [
+    ("ICP", 0, 0),
+    ("PLANE_ICP", 1, 0),
+    ("GICP", 2, 0),
+    ("HUBER_GICP", 2, 1),
+    ("CAUCHY_GICP", 2, 2),
+    ("HUBER_ICP", 0, 1),
+    ("CAUCHY_PLANE", 1, 2),
+]
+
+
+@pytest.fixture(scope="module")
+def golden_ctx(golden_prepared):
+    g = golden_prepared
+    ctx = load_ctx(g["target"], g["target_tree"], g["source"])
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,factor,robust", FACTORS)
+def test_linearize_and_error_golden(golden_prepared, golden_ctx, name, factor, robust):
+    g = golden_prepared
+    ctx = golden_ctx
+    reg = O.Registration(factor=factor, robust=robust, robust_c=0.7, num_threads=0)
+    tp, sp = g["target"].points, g["source"].points
+    for j, T in enumerate([np.eye(4), g["T"]] + noise_poses()[1:2]):
+        cpu = reg.linearize(g["target"], g["target_tree"], g["source"], T)
+        gpu = ctx.linearize(T, factor=factor, robust=robust, robust_c=0.7, max_dist_sq=1.0)
+        check_linearized(gpu, cpu, (name, j))
+        check_correspondences(ctx, reg, tp, sp, T)
+        assert abs(ctx.num_inliers() - int((reg.correspondences(len(sp)) != O.NO_INDEX).sum())) <= 2
+        # LM trial poses: cached correspondences, frozen precision matrices
+        for a in ([0.01, -0.02, 0.005, 0.05, -0.03, 0.02], [0, 0, 0, 0, 0, 0]):
+            T2 = T @ O.se3_exp(np.array(a, dtype=float))
+            e_cpu = reg.error(g["target"], g["source"], T2)
+            e_gpu = ctx.error(T2)
+            assert abs(e_gpu - e_cpu) <= RTOL * e_cpu, (name, j, e_gpu, e_cpu)
+
+
+def test_null_rejector_and_small_radius(golden_prepared, golden_ctx):
+    g = golden_prepared
+    sg = _sg()
+    for rej, md in ((O.REJECT_NONE, 1.0), (O.REJECT_DISTANCE, 0.05)):
+        reg = O.Registration(factor=O.FACTOR_GICP, rejector=rej, max_dist_sq=md, num_threads=0)
+        cpu = reg.linearize(g["target"], g["target_tree"], g["source"], np.eye(4))
+        gpu = golden_ctx.linearize(np.eye(4), factor=sg.FACTOR_GICP, rejector=rej, max_dist_sq=md)
+        check_linearized(gpu, cpu, ("rejector", rej))
+        if rej == O.REJECT_NONE:
+            assert golden_ctx.num_inliers() == len(g["source"])
+
+
+def test_own_tree_gives_same_result(golden_prepared):
+    """Exact NN does not depend on the tree's split choices (only exact ties do)."""
+    g = golden_prepared
+    a = load_ctx(g["target"], g["target_tree"], g["source"])
+    b = load_ctx(g["target"], None, g["source"], own_tree=True)
+    Ha, ba, ea = a.linearize(g["T"])
+    Hb, bb, eb = b.linearize(g["T"])
+    ca, cb = a.correspondences(), b.correspondences()
+    assert (ca != cb).sum() <= 2
+    assert np.linalg.norm(Ha - Hb) <= 1e-6 * np.linalg.norm(Ha) and abs(ea - eb) <= 1e-6 * ea
+    a.close()
+    b.close()
+
+
+def _gn_align(ctx, sg, factor, robust, init_T, max_iter=20, lam=1e-6):
+    """GaussNewtonOptimizer::optimize (registration/optimizer.hpp:24-63) on top of the C-ABI, host side in numpy."""
+    T = init_T.copy()
+    for i in range(max_iter):
+        H, b, e = ctx.linearize(T, factor=factor, robust=robust)
+        d = np.linalg.solve(H + lam * np.eye(6), -b)
+        T = T @ O.se3_exp(d)
+        if np.linalg.norm(d[:3]) <= 0.1 * np.pi / 180 and np.linalg.norm(d[3:]) <= 1e-3:
+            break
+    return T, i
+
+
+@pytest.mark.parametrize("name,factor,robust", FACTORS[:5])
+def test_converged_pose_matches_oracle(golden_prepared, golden_ctx, name, factor, robust):
+    g = golden_prepared
+    sg = _sg()
+    reg = O.Registration(factor=factor, robust=robust, num_threads=0)
+    reg.set_optimizer(type=O.OPT_GN)
+    for Tn in noise_poses()[:2]:
+        r = reg.align(g["target"], g["target_tree"], g["source"], Tn)
+        T, it = _gn_align(golden_ctx, sg, factor, robust, Tn)
+        rot, trans = pose_error(r.T_target_source, T)
+        assert rot < 1e-4 and trans < 1e-3, (name, rot, trans)
+        assert it == r.iterations
+        rot, trans = pose_error(g["T"], T)
+        assert rot < np.deg2rad(2.5) and trans < 0.2
+
+
+def test_voxelmap_target(golden_prepared):
+    g = golden_prepared
+    sg = _sg()
+    for offsets in (1, 7, 27):
+        vm = O.GaussianVoxelMap(g["target"], 1.0, offsets)
+        coords, means, covs, _ = vm.export()
+        ctx = sg.Context(0)
+        ctx.set_target_voxelmap(1.0, coords, means, covs, offsets)
+        ctx.set_source(g["source"].points, g["source"].covs)
+        reg = O.Registration(factor=O.FACTOR_GICP, num_threads=0)
+        for T in (np.eye(4), g["T"]):
+            cpu = reg.linearize(vm, None, g["source"], T)
+            gpu = ctx.linearize(T, factor=sg.FACTOR_GICP)
+            check_linearized(gpu, cpu, ("vgicp", offsets))
+            c = reg.correspondences(len(g["source"]))
+            assert (ctx.correspondences() != c).sum() <= 2
+            T2 = T @ O.se3_exp(np.array([0.01, 0.0, -0.01, 0.02, 0.02, 0.0]))
+            e_cpu, e_gpu = reg.error(vm, g["source"], T2), ctx.error(T2)
+            assert abs(e_gpu - e_cpu) <= RTOL * e_cpu
+        ctx.close()
+
+
+def test_empty_and_tiny_inputs(golden_prepared):
+    g = golden_prepared
+    sg = _sg()
+    ctx = sg.Context(0)
+    # empty source / empty target: zeros, no crash (helper_test.cpp:53-59, kdtree_test.cpp:170-176)
+    ctx.set_target(g["target"].points, g["target"].normals, g["target"].covs)
+    ctx.build_target_kdtree()
+    ctx.set_source(np.zeros((0, 4)), np.zeros((0, 4, 4)))
+    H, b, e = ctx.linearize(np.eye(4))
+    assert not H.any() and not b.any() and e == 0.0 and ctx.num_inliers() == 0
+    assert ctx.error(np.eye(4)) == 0.0
+    ctx.set_target(np.zeros((0, 4)), None, np.zeros((0, 4, 4)))
+    ctx.build_target_kdtree()
+    ctx.set_source(g["source"].points, g["source"].covs)
+    H, b, e = ctx.linearize(np.eye(4))
+    assert not H.any() and e == 0.0
+    assert np.all(ctx.correspondences() == sg.NO_CORRESPONDENCE)
+    # ragged sizes around the leaf size and the block size
+    for n in (1, 5, 19, 20, 21, 127, 129, 1000):
+        tp = g["target"].points[:n]
+        tc = O.Cloud(tp)
+        tt = O.KdTree(tc)
+        tc.set_features(g["target"].normals[:n], g["target"].covs[:n])
+        c2 = load_ctx(tc, tt, g["source"])
+        reg = O.Registration(factor=O.FACTOR_GICP, rejector=O.REJECT_NONE, num_threads=0)
+        cpu = reg.linearize(tc, tt, g["source"], g["T"])
+        gpu = c2.linearize(g["T"], rejector=sg.REJECT_NONE)
+        check_linearized(gpu, cpu, ("tiny", n))
+        c2.close()
+    # missing features are an error, not a silent fallback
+    ctx.set_target(g["target"].points)
+    ctx.build_target_kdtree()
+    with pytest.raises(sg.SgbError):
+        ctx.linearize(np.eye(4), factor=sg.FACTOR_GICP)
+    with pytest.raises(sg.SgbError):
+        ctx.linearize(np.eye(4), factor=sg.FACTOR_PLANE_ICP)
+    ctx.linearize(np.eye(4), factor=sg.FACTOR_ICP)
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def synthetic_pair():
+    from small_gicp_b200.synthetic import make_pair
+
+    tgt, src, T = make_pair(200_000)
+    nt = max(1, O.max_threads())
+    tc, sc = O.Cloud(tgt), O.Cloud(src)
+    tt, st = O.KdTree(tc), O.KdTree(sc)
+    tt.estimate(20, O.FEAT_NORMAL_COV, nt)
+    st.estimate(20, O.FEAT_COV, nt)
+    return tc, tt, sc, T, nt
+
+
+def test_synthetic_200k_gicp(synthetic_pair):
+    """BASELINE config 2 shape (synthetic room pair, GICP, GN) at a size the oracle finishes in seconds."""
+    tc, tt, sc, Tgt, nt = synthetic_pair
+    sg = _sg()
+    ctx = load_ctx(tc, tt, sc)
+    reg = O.Registration(factor=O.FACTOR_GICP, num_threads=nt)
+    reg.set_optimizer(type=O.OPT_GN)
+    tp, sp = tc.points, sc.points
+    for T in (np.eye(4), Tgt):
+        cpu = reg.linearize(tc, tt, sc, T)
+        gpu = ctx.linearize(T)
+        check_linearized(gpu, cpu, "synthetic")
+        check_correspondences(ctx, reg, tp, sp, T)
+    r = reg.align(tc, tt, sc, np.eye(4))
+    T, it = _gn_align(ctx, sg, sg.FACTOR_GICP, sg.ROBUST_NONE, np.eye(4))
+    rot, trans = pose_error(r.T_target_source, T)
+    assert rot < 1e-4 and trans < 1e-3, (rot, trans)
+    rot, trans = pose_error(Tgt, T)
+    assert rot < 2e-3 and trans < 2e-2, (rot, trans)
+    # own tree: same sums
+    ctx2 = load_ctx(tc, None, sc, own_tree=True)
+    H1, b1, e1 = ctx.linearize(Tgt)
+    H2, b2, e2 = ctx2.linearize(Tgt)
+    assert np.linalg.norm(H1 - H2) <= 1e-6 * np.linalg.norm(H1) and abs(e1 - e2) <= 1e-6 * e1
+    # determinism: bitwise identical on repeat
+    H3, b3, e3 = ctx.linearize(Tgt)
+    assert np.array_equal(H1, H3) and np.array_equal(b1, b3) and e1 == e3
+    ctx.close()
+    ctx2.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 full size (1M x 1M): size-independent properties instead of an oracle run.
+      * own-tree NN == brute-force NN on a random sample of queries (exactness)
+      * linearity: sums over two disjoint halves of the source add up to the sum over the whole
+      * error(T_lin) == e of linearize; H symmetric positive definite
+    """
+    import torch
+
+    from small_gicp_b200.synthetic import make_pair
+
+    sg = _sg()
+    n = 1_000_000
+    tgt, src, Tgt = make_pair(n)
+    ctx = sg.Context(0)
+    ctx.set_target(tgt)
+    ctx.build_target_kdtree()
+    ctx.set_source(src)
+    H, b, e = ctx.linearize(Tgt, factor=sg.FACTOR_ICP)
+    corr = ctx.correspondences()
+    assert abs(ctx.error(Tgt) - e) <= 1e-9 * e
+    assert np.linalg.eigvalsh(H).min() > 0
+    # exactness on a sample, brute force in torch on the GPU (float64)
+    rng = np.random.default_rng(0)
+    sample = rng.choice(n, 2000, replace=False)
+    q = torch.tensor((src[sample] @ Tgt[:3, :3].T + Tgt[:3, 3]), device="cuda")
+    P = torch.tensor(tgt, device="cuda")
+    d2 = torch.cdist(q, P).min(dim=1)
+    bf_idx = d2.indices.cpu().numpy()
+    bf_d2 = (d2.values.cpu().numpy()) ** 2
+    got = corr[sample]
+    inl = bf_d2 <= 1.0
+    assert np.all((got != sg.NO_CORRESPONDENCE) == inl) or np.abs(bf_d2[(got != sg.NO_CORRESPONDENCE) != inl] - 1.0).max() < 1e-4
+    both = inl & (got != sg.NO_CORRESPONDENCE)
+    mism = both & (got != bf_idx.astype(np.uint64))
+    if mism.any():
+        qq = q.cpu().numpy()[mism]
+        dg = ((tgt[got[mism].astype(np.int64)] - qq) ** 2).sum(1)
+        assert np.all(np.abs(dg - bf_d2[mism]) <= 1e-5 * bf_d2[mism] + 1e-7)
+    assert mism.sum() <= 5
+    # linearity over a split of the source
+    half = n // 2
+    ctx.set_source(src[:half])
+    Ha, ba, ea = ctx.linearize(Tgt, factor=sg.FACTOR_ICP)
+    ctx.set_source(src[half:])
+    Hb, bb, eb = ctx.linearize(Tgt, factor=sg.FACTOR_ICP)
+    # (each call re-centres its source box, so FP32 roundings differ slightly between the split and the whole)
+    assert np.linalg.norm(Ha + Hb - H) <= 1e-6 * np.linalg.norm(H)
+    assert abs(ea + eb - e) <= 1e-6 * e
+    ctx.close()
