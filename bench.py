@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--covs", default="knn", choices=["knn", "analytic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--leaf", type=int, default=0, help="max leaf size of the device kd-tree (0 = library default)")
     return ap.parse_args()
 
 
@@ -273,10 +274,14 @@ def run_ours(args):
     inp = make_inputs(args.points, rank, args.covs)
     n_src = inp["source"].shape[0]
     ctx = sg.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for everything: the context's kernels, torch's fills / events and NCCL all
+    # run on it, so CUDA events recorded on it bracket exactly the work being timed
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx.set_target(inp["target"], None, inp["target_covs"])
-    ctx.build_target_kdtree()
+    ctx.build_target_kdtree(args.leaf)
     # pinned host copies of the step's inputs for the e2e leg
     src_pin = torch.from_numpy(inp["source"]).pin_memory()
     cov_pin = torch.from_numpy(inp["source_covs"]).pin_memory()

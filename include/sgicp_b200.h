@@ -105,6 +105,25 @@ int sgb_correspondences(sgb_ctx* ctx, uint64_t* target_index);
 /* count_if(factors, inlier()) of the last linearize (registration/optimizer.hpp:60,146). */
 int sgb_num_inliers(sgb_ctx* ctx, size_t* n);
 
+/* ---- per-cloud preparation on the device (not per-iteration) --------------------
+ * sgb_estimate_features replaces estimate_normals / estimate_covariances / estimate_normals_covariances and
+ * their _omp / _tbb variants (include/small_gicp/util/normal_estimation.hpp:12-140, normal_estimation_omp.hpp:9-60):
+ * k nearest neighbours of every point in the cloud's own kd-tree (the point itself included), local covariance,
+ * smallest-eigenvalue direction -> normal (flipped toward the origin, w = 0) and covariance with eigenvalues replaced
+ * by (1e-3, 1, 1); fewer than 5 neighbours -> zero normal / identity covariance.  Either output may be NULL.
+ * num_neighbors in 1..32. */
+int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points_xyz1, int num_neighbors, double* out_normals_xyz0 /*or NULL*/,
+                          double* out_covs_4x4 /*or NULL*/);
+/* Device-resident variants: fill the normals + covariances of the CURRENT target (after its kd-tree is set/built) or
+ * the covariances of the CURRENT source without any host round trip (frame streams, benchmark_odom.hpp:59 +
+ * odometry_benchmark_small_gicp_tbb.cpp:26-27). */
+int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors);
+int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors);
+/* replaces voxelgrid_sampling{,_omp,_tbb} (include/small_gicp/util/downsampling.hpp:22-78): one output point per occupied
+ * voxel = mean of its points, voxels ordered by the reference's 63-bit key (x | y<<21 | z<<42 of floor(p/leaf)+2^20);
+ * points whose voxel coordinate leaves the 21-bit range are dropped.  out_points_xyz1 must hold n points. */
+int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points_xyz1, double leaf_size, double* out_points_xyz1, size_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

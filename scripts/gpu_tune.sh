@@ -1,0 +1,26 @@
+#!/bin/bash
+TAG=${1:-r01e}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest -m gpu" | tee $OUT/pytest.log
+timeout 1200 python -m pytest tests -q -m gpu >> $OUT/pytest.log 2>&1; echo "rc=$?" >> $OUT/pytest.log
+tail -8 $OUT/pytest.log
+show() {
+python - <<PY
+import json
+try:
+    d=json.load(open("$1"))
+    print("$2 value", round(d["value"],1), "ms", round(d["ms_per_step"],4), "kernel_ms", round(d["roofline"]["kernel_ms"],4), "warm", round(d["value_l2_warm"],1), "e2e", round(d["e2e"]["value"],1), "launches", d["gpu_launches"], "iters", d["pose_error_vs_gt"]["gn_iterations"])
+except Exception as e:
+    print("fail", e); print(open("$1".replace(".json",".err")).read()[-1500:])
+PY
+}
+for mode in 2 1; do for leaf in 20 32 64; do
+  name=m${mode}_l${leaf}
+  SGB_SEARCH=$mode timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --leaf $leaf > $OUT/bench_$name.json 2> $OUT/bench_$name.err
+  show $OUT/bench_$name.json "mode=$mode leaf=$leaf"
+done; done
+echo "== ncu full capture (packet)"
+SGB_SEARCH=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"packet_search_kernel|factor_reduce_kernel" -s 16 -c 4 -f -o $OUT/prof_packet \
+    python bench.py --steps 4 --warmup 1 --no-cpu-baseline --leaf 32 > $OUT/ncu_full.log 2>&1
+echo "rc=$?"

@@ -39,6 +39,10 @@ _SIGNATURES = {
     "sgb_error_device": (C.c_int, [_vp, _dp, _vp]),
     "sgb_correspondences": (C.c_int, [_vp, _u64p]),
     "sgb_num_inliers": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "sgb_estimate_features": (C.c_int, [_vp, C.c_size_t, _dp, C.c_int, _dp, _dp]),
+    "sgb_target_estimate_features": (C.c_int, [_vp, C.c_int]),
+    "sgb_source_estimate_features": (C.c_int, [_vp, C.c_int]),
+    "sgb_voxelgrid_sampling": (C.c_int, [_vp, C.c_size_t, _dp, C.c_double, _dp, C.POINTER(C.c_size_t)]),
 }
 
 
@@ -208,3 +212,26 @@ class Context:
         n = C.c_size_t(0)
         self._check(self._L.sgb_num_inliers(self._h, C.byref(n)))
         return int(n.value)
+
+    # ---- per-cloud preparation on the device ----
+    def estimate_features(self, points, num_neighbors=20, normals=True, covs=True):
+        """estimate_normals_covariances (util/normal_estimation.hpp): returns (normals (N,4) | None, covs (N,4,4) | None)"""
+        p = _points4(points)
+        n_out = np.empty((p.shape[0], 4)) if normals else None
+        c_out = np.empty((p.shape[0], 4, 4)) if covs else None
+        self._check(self._L.sgb_estimate_features(self._h, p.shape[0], _d(p), int(num_neighbors), _d(n_out), _d(c_out)))
+        return n_out, c_out
+
+    def estimate_target_features(self, num_neighbors=20):
+        self._check(self._L.sgb_target_estimate_features(self._h, int(num_neighbors)))
+
+    def estimate_source_features(self, num_neighbors=20):
+        self._check(self._L.sgb_source_estimate_features(self._h, int(num_neighbors)))
+
+    def voxelgrid_sampling(self, points, leaf_size):
+        """voxelgrid_sampling (util/downsampling.hpp:22-78): returns the (M,4) down-sampled points"""
+        p = _points4(points)
+        out = np.empty_like(p)
+        m = C.c_size_t(0)
+        self._check(self._L.sgb_voxelgrid_sampling(self._h, p.shape[0], _d(p), float(leaf_size), _d(out), C.byref(m)))
+        return out[: int(m.value)].copy()

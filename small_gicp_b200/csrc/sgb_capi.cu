@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/sgicp_b200.h"
+#include "sgb_context.hpp"
 #include "sgb_kdtree_host.hpp"
 #include "sgb_kernels.h"
 
@@ -18,87 +19,6 @@ using namespace sgb;
 namespace {
 
 thread_local std::string g_create_error;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    const size_t want = bytes + bytes / 8 + 256;  // slack so streams of slightly varying frames do not realloc
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <typename T>
-  T* as() const {
-    return static_cast<T*>(p);
-  }
-};
-
-}  // namespace
-
-struct sgb_ctx {
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  uint64_t launches = 0;
-
-  // ---- target ----
-  size_t n_tgt = 0;
-  bool tgt_has_normals = false, tgt_has_covs = false;
-  bool tgt_is_voxel = false, tgt_ready = false;
-  DevBuf tgt_orig_pts, tgt_orig_normals, tgt_orig_covA, tgt_orig_covB;  // original order
-  DevBuf tgt_pts, tgt_normals, tgt_covA, tgt_covB;                      // leaf order (or voxel order)
-  DevBuf tgt_nodes, tgt_perm;
-  int tree_depth = 0;
-  DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
-  DevBuf vox_table;
-  uint32_t vox_mask = 0;
-  int vox_offsets = 1;
-  double vox_inv_leaf = 1.0;
-
-  // ---- source ----
-  size_t n_src = 0;
-  bool src_has_covs = false;
-  DevBuf src_pts, src_covA, src_covB, src_perm, src_centre, src_bounds;
-
-  // ---- scratch ----
-  DevBuf stage_pts, stage_normals, stage_covs;  // raw double uploads
-  DevBuf tmp_pts, tmp_covA, tmp_covB, keys_in, keys_out, vals_in, sort_temp;
-  DevBuf corr, partials, ticket, out44, corr64;
-  double* h_out = nullptr;  // pinned, 64 doubles
-
-  // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
-  bool have_lin = false;
-  int lin_factor = 0, lin_robust = 0;
-  double lin_c = 1.0;
-  double Tlin[12];
-  const double* last_out = nullptr;  // device pointer holding H|b|e|inliers of the last linearize
-  int lin_grid = 0;
-};
-
-namespace {
-
-int fail(sgb_ctx* c, int code, const std::string& msg) {
-  if (c) c->err = msg;
-  return code;
-}
-
-#define CU(expr)                                                                                            \
-  do {                                                                                                      \
-    cudaError_t _e = (expr);                                                                                \
-    if (_e != cudaSuccess) return fail(ctx, 2, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
-  } while (0)
 
 inline void pose_from_colmajor(const double* T, double out12[12]) {
   for (int i = 0; i < 3; i++) {
@@ -125,7 +45,14 @@ int ensure_reduction_buffers(sgb_ctx* ctx, int grid) {
   return 0;
 }
 
-int upload_tree(sgb_ctx* ctx, const FlatTree& tree) {
+int upload_tree(sgb_ctx* ctx, const FlatTree& tree, const float* host_pts_xyzw) {
+  // packet (BVH2) records of the same tree for the warp-cooperative search
+  std::vector<PacketNode> pnodes;
+  int pending = 1;
+  build_packet_nodes(tree, host_pts_xyzw, pnodes, &pending);
+  if (pending > 40) return fail(ctx, 1, "kd-tree too deep for the device traversal stack (depth > 40)");
+  CU(ctx->tgt_pnodes.reserve(pnodes.size() * sizeof(PacketNode)));
+  CU(cudaMemcpyAsync(ctx->tgt_pnodes.p, pnodes.data(), pnodes.size() * sizeof(PacketNode), cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx->tgt_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
   CU(ctx->tgt_perm.reserve(tree.perm.size() * sizeof(uint32_t)));
   CU(cudaMemcpyAsync(ctx->tgt_nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, ctx->stream));
@@ -148,6 +75,7 @@ int upload_tree(sgb_ctx* ctx, const FlatTree& tree) {
   ctx->tgt_is_voxel = false;
   ctx->tgt_ready = true;
   ctx->have_lin = false;
+  ctx->corr_seeds = false;
   return 0;
 }
 
@@ -168,6 +96,7 @@ int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
   P.src.covB = ctx->src_covB.as<float4>();
   P.src.centre = ctx->src_centre.as<double>();
   P.src.n = static_cast<uint32_t>(ctx->n_src);
+  P.src.run = ctx->src_run;
   pose_from_colmajor(T_colmajor16, P.T);
   P.corr = ctx->corr.as<uint32_t>();
   P.partials = ctx->partials.as<double>();
@@ -208,17 +137,42 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
   LinParams P;
   fill_params(ctx, P, T);
   std::memcpy(P.Tlin, P.T, sizeof(P.T));
+  // FP32 search bound a hair above the threshold; the rejector itself (d2 > max, rejector.hpp:24) is applied to the FP64 residual
   float bound = FLT_MAX;
+  P.max_dist_sq_d = DBL_MAX;
   if (rejector == SGB_REJECT_DISTANCE) {
-    bound = nextafterf(static_cast<float>(max_dist_sq), INFINITY);  // accept d2 <= max (rejector.hpp:24 rejects d2 > max)
+    bound = nextafterf(static_cast<float>(max_dist_sq * (1.0 + 4e-6) + 1e-12), INFINITY);
     if (!(bound < FLT_MAX)) bound = FLT_MAX;
+    P.max_dist_sq_d = max_dist_sq;
   }
   P.max_dist_sq = bound;
+  P.use_prev = (ctx->corr_seeds && !ctx->tgt_is_voxel) ? 1 : 0;
   P.robust_c = robust_c;
   P.out = d_out;
-  CU(launch_linearize(P, factor, robust, ctx->tgt_is_voxel, grid, depth, ctx->stream));
-  ctx->launches += 1;
+  if (ctx->search_mode != 0 && !ctx->tgt_is_voxel) {
+    // phase 1: search at high occupancy; phase 2: factor algebra + reduction (sgb_kernels_split.cu)
+    const uint32_t chunk_pts = 32u * ctx->src_run;
+    const size_t n_chunks = (ctx->n_src + chunk_pts - 1) / chunk_pts;
+    int sgrid = static_cast<int>((n_chunks * 32 + kLinBlock - 1) / kLinBlock);
+    if (ctx->search_mode == 2 && ctx->src_run == 1) {
+      const int scap = ctx->sm_count * packet_occupancy(depth);
+      if (sgrid > scap) sgrid = scap;
+      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, ctx->stream));
+    } else {
+      const int scap = ctx->sm_count * search_occupancy(depth);
+      if (sgrid > scap) sgrid = scap;
+      CU(launch_search(P, sgrid, depth, ctx->stream));
+    }
+    int fgrid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
+    if (fgrid > grid) fgrid = grid;
+    CU(launch_factor_reduce(P, factor, robust, fgrid, ctx->stream));
+    ctx->launches += 2;
+  } else {
+    CU(launch_linearize(P, factor, robust, ctx->tgt_is_voxel, grid, depth, ctx->stream));
+    ctx->launches += 1;
+  }
   ctx->have_lin = true;
+  ctx->corr_seeds = true;
   ctx->lin_factor = factor;
   ctx->lin_robust = robust;
   ctx->lin_c = robust_c;
@@ -294,6 +248,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
     return 2;
   }
   ctx->stream = ctx->own_stream;
+  if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
   *out_ctx = ctx;
   return 0;
 }
@@ -303,9 +258,10 @@ void sgb_destroy(sgb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->tgt_orig_pts, &ctx->tgt_orig_normals, &ctx->tgt_orig_covA, &ctx->tgt_orig_covB, &ctx->tgt_pts,  &ctx->tgt_normals, &ctx->tgt_covA,
-                    &ctx->tgt_covB,     &ctx->tgt_nodes,        &ctx->tgt_perm,      &ctx->tgt_centre,    &ctx->tgt_bounds, &ctx->vox_table, &ctx->src_pts,
+                    &ctx->tgt_covB,     &ctx->tgt_nodes,        &ctx->tgt_perm, &ctx->tgt_pnodes,     &ctx->tgt_centre,    &ctx->tgt_bounds, &ctx->vox_table, &ctx->src_pts,
                     &ctx->src_covA,     &ctx->src_covB,         &ctx->src_perm,      &ctx->src_centre,    &ctx->src_bounds, &ctx->stage_pts, &ctx->stage_normals,
                     &ctx->stage_covs,   &ctx->tmp_pts,          &ctx->tmp_covA,      &ctx->tmp_covB,      &ctx->keys_in,  &ctx->keys_out,    &ctx->vals_in,
+                    &ctx->pre_pts, &ctx->pre_leaf_pts, &ctx->pre_nodes, &ctx->pre_perm, &ctx->pre_centre, &ctx->pre_bounds, &ctx->pre_out_normals, &ctx->pre_out_covs, &ctx->pre_heads, &ctx->pre_slots, &ctx->pre_vals_out,
                     &ctx->sort_temp,    &ctx->corr,             &ctx->partials,      &ctx->ticket,        &ctx->out44,    &ctx->corr64};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -346,6 +302,7 @@ int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   ctx->tgt_ready = false;
   ctx->tgt_is_voxel = false;
   ctx->have_lin = false;
+  ctx->corr_seeds = false;
   CU(ctx->tgt_centre.reserve(4 * sizeof(double)));
   CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
@@ -386,7 +343,10 @@ int sgb_target_set_kdtree(sgb_ctx* ctx, const void* nodes24, size_t n_nodes, uin
   FlatTree tree;
   std::string err;
   if (!flatten_reference_tree(nodes24, n_nodes, root, indices, ctx->n_tgt, centre, tree, err)) return fail(ctx, 1, "sgb_target_set_kdtree: " + err);
-  return upload_tree(ctx, tree);
+  std::vector<float> pts(ctx->n_tgt * 4);  // centred FP32 points, for the children bounding boxes
+  CU(cudaMemcpyAsync(pts.data(), ctx->tgt_orig_pts.p, ctx->n_tgt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return upload_tree(ctx, tree, pts.data());
 }
 
 int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
@@ -402,7 +362,7 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
   FlatTree tree;
   std::string err;
   if (!build_flat_tree(pts.data(), ctx->n_tgt, max_leaf_size, tree, err)) return fail(ctx, 1, "sgb_target_build_kdtree: " + err);
-  return upload_tree(ctx, tree);
+  return upload_tree(ctx, tree, pts.data());
 }
 
 int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, const int32_t* coords, const double* means, const double* covs, int search_offsets) {
@@ -418,6 +378,7 @@ int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, con
   ctx->tgt_is_voxel = true;
   ctx->tgt_ready = true;
   ctx->have_lin = false;
+  ctx->corr_seeds = false;
   ctx->vox_offsets = search_offsets;
   ctx->vox_inv_leaf = 1.0 / leaf_size;
   CU(ctx->tgt_centre.reserve(4 * sizeof(double)));
@@ -470,6 +431,7 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   ctx->n_src = n;
   ctx->src_has_covs = covs != nullptr;
   ctx->have_lin = false;
+  ctx->corr_seeds = false;
   CU(ctx->src_centre.reserve(4 * sizeof(double)));
   CU(ctx->src_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
@@ -500,6 +462,17 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   CU(ctx->sort_temp.reserve(temp_bytes));
   CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
                         ctx->src_perm.as<uint32_t>(), n, ctx->stream));
+  // chunk-transposed Morton order: a lane walks K consecutive points of the curve, warp loads stay coalesced.
+  // K shrinks for small clouds so that there are still enough 32*K-point work units to fill the GPU.
+  uint32_t K = 1;
+  if (const char* s = getenv("SGB_RUN")) K = static_cast<uint32_t>(atoi(s)) > 0 ? static_cast<uint32_t>(atoi(s)) : 1;  // profiling switch
+  while (K > 1 && n / (32ull * K) < static_cast<size_t>(ctx->sm_count) * 16) K >>= 1;
+  ctx->src_run = K;
+  if (K > 1) {
+    CU(launch_chunk_transpose(ctx->src_perm.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), n, K, ctx->sm_count, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->src_perm.p, ctx->vals_in.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += 1;
+  }
   CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_pts.as<float4>(), ctx->src_pts.as<float4>(), covs ? ctx->tmp_covA.as<float4>() : nullptr,
                    ctx->src_covA.as<float4>(), covs ? ctx->tmp_covB.as<float4>() : nullptr, ctx->src_covB.as<float4>(), nullptr, nullptr, ctx->sm_count,
                    ctx->stream));

@@ -1,0 +1,163 @@
+// SPDX-License-Identifier: MIT
+// C-ABI entry points of the per-cloud preparation steps: normal / covariance estimation and
+// voxel-grid down-sampling on the device.  Kernels: sgb_preprocess.cu.
+#include <cstring>
+#include <vector>
+
+#include "../../include/sgicp_b200.h"
+#include "sgb_context.hpp"
+#include "sgb_kdtree_host.hpp"
+#include "sgb_kernels.h"
+
+using namespace sgb;
+
+namespace {
+
+constexpr int kFeatureLeaf = 10;  // leaf size of the throw-away tree used for the k-NN of the features
+
+/// Build this library's kd-tree over `n` centred float4 points that live on the device in original order;
+/// leaves `pre_nodes`, `pre_leaf_pts` (leaf order, w = original index) on the device and returns the depth.
+int build_feature_tree(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, int* depth_out) {
+  std::vector<float> pts(n * 4);
+  CU(cudaMemcpyAsync(pts.data(), d_orig_pts, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  FlatTree tree;
+  std::string err;
+  if (!build_flat_tree(pts.data(), n, kFeatureLeaf, tree, err)) return fail(ctx, 1, "feature kd-tree: " + err);
+  CU(ctx->pre_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
+  CU(ctx->pre_perm.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_leaf_pts.reserve(n * sizeof(float4)));
+  CU(cudaMemcpyAsync(ctx->pre_nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->pre_perm.p, tree.perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_gather(ctx->pre_perm.as<uint32_t>(), n, d_orig_pts, ctx->pre_leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                   ctx->sm_count, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // host vectors die at return
+  ctx->launches += 1;
+  *depth_out = tree.depth;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_neighbors, double* out_normals, double* out_covs) {
+  if (!ctx) return 1;
+  if (n && !points) return fail(ctx, 1, "sgb_estimate_features: null points");
+  if (num_neighbors < 1 || num_neighbors > 32) return fail(ctx, 1, "sgb_estimate_features: num_neighbors must be in 1..32");
+  if (n >= (1ull << 30)) return fail(ctx, 1, "sgb_estimate_features: too many points");
+  if (n == 0 || (!out_normals && !out_covs)) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->pre_centre.reserve(4 * sizeof(double)));
+  CU(ctx->pre_bounds.reserve(6 * sizeof(double)));
+  CU(ctx->pre_pts.reserve(n * sizeof(float4)));
+  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->pre_bounds.as<double>(), ctx->pre_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, nullptr, n, ctx->pre_centre.as<double>(), ctx->pre_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr,
+                    nullptr, ctx->sm_count, ctx->stream));
+  ctx->launches += 4;
+  int depth = 0;
+  if (int rc = build_feature_tree(ctx, ctx->pre_pts.as<float4>(), n, &depth)) return rc;
+  if (out_normals) CU(ctx->pre_out_normals.reserve(n * 4 * sizeof(double)));
+  if (out_covs) CU(ctx->pre_out_covs.reserve(n * 16 * sizeof(double)));
+  const int mode = (out_normals ? 1 : 0) | (out_covs ? 2 : 0);
+  CU(launch_features(ctx->pre_nodes.as<KdNode>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->pre_centre.as<double>(), mode,
+                     nullptr, nullptr, nullptr, out_normals ? ctx->pre_out_normals.as<double>() : nullptr, out_covs ? ctx->pre_out_covs.as<double>() : nullptr,
+                     depth, 0, ctx->stream));
+  ctx->launches += 1;
+  if (out_normals) CU(cudaMemcpyAsync(out_normals, ctx->pre_out_normals.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_covs) CU(cudaMemcpyAsync(out_covs, ctx->pre_out_covs.p, n * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors) {
+  if (!ctx) return 1;
+  if (num_neighbors < 1 || num_neighbors > 32) return fail(ctx, 1, "sgb_target_estimate_features: num_neighbors must be in 1..32");
+  if (ctx->tgt_is_voxel || !ctx->tgt_ready) return fail(ctx, 1, "sgb_target_estimate_features: needs a point target with its kd-tree (set points, then set/build the tree)");
+  const size_t n = ctx->n_tgt;
+  ctx->tgt_has_normals = ctx->tgt_has_covs = true;
+  ctx->have_lin = false;
+  ctx->corr_seeds = false;
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->tgt_normals.reserve(n * sizeof(float4)));
+  CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
+  CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
+  // the target's own tree and leaf-ordered points are already resident: write the features straight into the leaf-ordered streams
+  CU(launch_features(ctx->tgt_nodes.as<KdNode>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->tgt_centre.as<double>(), 3,
+                     ctx->tgt_normals.as<float4>(), ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->tree_depth, 1, ctx->stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors) {
+  if (!ctx) return 1;
+  if (num_neighbors < 1 || num_neighbors > 32) return fail(ctx, 1, "sgb_source_estimate_features: num_neighbors must be in 1..32");
+  const size_t n = ctx->n_src;
+  ctx->src_has_covs = true;
+  ctx->have_lin = false;
+  ctx->corr_seeds = false;
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  // tmp_pts still holds the source in ORIGINAL order (centred FP32, w = index) from sgb_source_set_points
+  int depth = 0;
+  if (int rc = build_feature_tree(ctx, ctx->tmp_pts.as<float4>(), n, &depth)) return rc;
+  CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
+  CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
+  CU(ctx->src_covA.reserve(n * sizeof(float4)));
+  CU(ctx->src_covB.reserve(n * sizeof(float4)));
+  CU(launch_features(ctx->pre_nodes.as<KdNode>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->src_centre.as<double>(), 2, nullptr,
+                     ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), nullptr, nullptr, depth, 0, ctx->stream));
+  // original order -> the search order of the source (chunk-transposed Morton)
+  CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_covA.as<float4>(), ctx->src_covA.as<float4>(), ctx->tmp_covB.as<float4>(), ctx->src_covB.as<float4>(),
+                   nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream));
+  ctx->launches += 2;
+  return 0;
+}
+
+int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points, double leaf_size, double* out_points, size_t* n_out) {
+  if (!ctx || !n_out) return 1;
+  *n_out = 0;
+  if (n && (!points || !out_points)) return fail(ctx, 1, "sgb_voxelgrid_sampling: null buffer");
+  if (!(leaf_size > 0.0)) return fail(ctx, 1, "sgb_voxelgrid_sampling: leaf_size must be positive");
+  if (n >= (1ull << 31)) return fail(ctx, 1, "sgb_voxelgrid_sampling: too many points");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_vals_out.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_heads.reserve((n + 1) * sizeof(uint32_t)));
+  CU(ctx->pre_slots.reserve((n + 1) * sizeof(uint32_t)));
+  CU(ctx->stage_covs.reserve(n * 4 * sizeof(double)));  // output staging (re-uses a scratch buffer)
+  CU(launch_voxel_keys(ctx->stage_pts.as<double>(), n, 1.0 / leaf_size, ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  size_t temp_bytes = 0;
+  CU(sort_pairs_u64_u32(nullptr, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->pre_vals_out.as<uint32_t>(), n, ctx->stream));
+  size_t scan_bytes = 0;
+  CU(exclusive_sum_u32(nullptr, scan_bytes, ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n + 1, ctx->stream));
+  CU(ctx->sort_temp.reserve(temp_bytes > scan_bytes ? temp_bytes : scan_bytes));
+  CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->pre_vals_out.as<uint32_t>(), n, ctx->stream));
+  CU(cudaMemsetAsync(ctx->pre_heads.p, 0, (n + 1) * sizeof(uint32_t), ctx->stream));
+  CU(launch_voxel_heads(ctx->keys_out.as<uint64_t>(), n, ctx->pre_heads.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  CU(exclusive_sum_u32(ctx->sort_temp.p, scan_bytes, ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n + 1, ctx->stream));
+  CU(launch_voxel_means(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n,
+                        ctx->stage_pts.as<double>(), ctx->stage_covs.as<double>(), ctx->sm_count, ctx->stream));
+  ctx->launches += 8;
+  uint32_t count = 0;
+  CU(cudaMemcpyAsync(&count, ctx->pre_slots.as<uint32_t>() + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (count) {
+    CU(cudaMemcpyAsync(out_points, ctx->stage_covs.p, static_cast<size_t>(count) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  *n_out = count;
+  return 0;
+}
+
+}  // extern "C"

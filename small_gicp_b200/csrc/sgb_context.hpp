@@ -1,0 +1,99 @@
+// SPDX-License-Identifier: MIT
+// The context behind the opaque sgb_ctx handle of include/sgicp_b200.h (shared by sgb_capi.cu / sgb_capi_preprocess.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace sgb {
+
+/// Grow-only device buffer (re-used across calls so that streams of similarly sized frames never reallocate).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+}  // namespace sgb
+
+struct sgb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int search_mode = 2;  // 2: packet (warp-cooperative) search + factor kernel; 1: per-thread search + factor kernel; 0: single fused kernel
+
+  // ---- target ----
+  size_t n_tgt = 0;
+  bool tgt_has_normals = false, tgt_has_covs = false;
+  bool tgt_is_voxel = false, tgt_ready = false;
+  sgb::DevBuf tgt_orig_pts, tgt_orig_normals, tgt_orig_covA, tgt_orig_covB;  // original order
+  sgb::DevBuf tgt_pts, tgt_normals, tgt_covA, tgt_covB;                      // leaf order (or voxel order)
+  sgb::DevBuf tgt_nodes, tgt_perm, tgt_pnodes;  // kd nodes (8 B), leaf permutation, packet records (64 B / inner node)
+  int tree_depth = 0;
+  sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
+  sgb::DevBuf vox_table;
+  uint32_t vox_mask = 0;
+  int vox_offsets = 1;
+  double vox_inv_leaf = 1.0;
+
+  // ---- source ----
+  size_t n_src = 0;
+  bool src_has_covs = false;
+  sgb::DevBuf src_pts, src_covA, src_covB, src_perm, src_centre, src_bounds;
+  uint32_t src_run = 1;  // K of the chunk-transposed source layout (DevSource::run)
+
+  // ---- scratch ----
+  sgb::DevBuf stage_pts, stage_normals, stage_covs;  // raw double uploads
+  sgb::DevBuf tmp_pts, tmp_covA, tmp_covB, keys_in, keys_out, vals_in, sort_temp;
+  sgb::DevBuf corr, partials, ticket, out44, corr64;
+  double* h_out = nullptr;  // pinned, 64 doubles
+
+  // ---- preprocessing scratch (sgb_capi_preprocess.cu) ----
+  sgb::DevBuf pre_pts, pre_leaf_pts, pre_nodes, pre_perm, pre_centre, pre_bounds, pre_out_normals, pre_out_covs, pre_heads, pre_slots, pre_vals_out;
+
+  // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
+  bool have_lin = false;
+  bool corr_seeds = false;  // corr[] holds correspondences of the current (target, tree, source) triple
+  int lin_factor = 0, lin_robust = 0;
+  double lin_c = 1.0;
+  double Tlin[12];
+  const double* last_out = nullptr;  // device pointer holding H|b|e|inliers of the last linearize
+  int lin_grid = 0;
+};
+
+namespace sgb {
+
+inline int fail(sgb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+}  // namespace sgb
+
+#define CU(expr)                                                                                                 \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if (_e != cudaSuccess) return sgb::fail(ctx, 2, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+  } while (0)

@@ -36,6 +36,8 @@ struct DevSource {
   const float4* covB;
   const double* centre;  // 3 doubles, device
   uint32_t n;
+  uint32_t run;  // K: source positions chunk*32K + k*32 + lane hold Morton ranks chunk*32K + lane*K + k (full chunks),
+                 // i.e. one lane walks K spatially consecutive points while every load of the warp stays coalesced
 };
 
 struct LinParams {
@@ -43,7 +45,9 @@ struct LinParams {
   DevSource src;
   double T[12];      // row-major R (9) then t (3): T_target_source of this call
   double Tlin[12];   // pose of the last linearize (error kernel, GICP precision matrix)
-  float max_dist_sq;  // seeded search bound (FLT_MAX for NullRejector)
+  float max_dist_sq;     // search bound in FP32, a hair above the rejector's threshold (FLT_MAX for NullRejector)
+  double max_dist_sq_d;  // the rejector's threshold itself, applied to the FP64 residual (DBL_MAX for NullRejector)
+  int use_prev;          // corr[] holds the previous linearize's correspondences for the same clouds: use them as search seeds
   double robust_c;
   uint32_t* corr;     // per source point (Morton order): leaf-order position / voxel id, or kNone
   double* partials;   // gridDim.x * kPartialStride
@@ -181,21 +185,25 @@ __device__ __forceinline__ void accumulate_factor(const double* R, const Sym3& M
 /// `best_d` enters as the search bound (only strictly closer points are accepted, knn_result.hpp:81-83).
 /// stack: shared memory, entry (s, lane) at stack[s * kLinBlock + threadIdx.x].
 __device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, float qx, float qy, float qz,
-                                               float& best_d, uint2* stack) {
-  uint32_t best = kNone;
+                                               float& best_d, uint32_t best, uint2* stack) {
+  // `best` / `best_d` may enter seeded with a candidate (an upper bound only prunes: the result is still the
+  // exact nearest neighbour, the seed wins only if nothing is strictly closer).
   uint32_t node = 0;
   int sp = 0;
   uint2* my_stack = stack + threadIdx.x;
   for (;;) {
     KdNode nd = __ldg(&nodes[node]);
     uint32_t kind = nd.y & 3u;
-    while (kind != 3u) {  // descend, remembering the far child and its plane distance
+    while (kind != 3u) {  // descend; remember the far child only if the current bound does not already prune it
       const float qv = kind == 0u ? qx : (kind == 1u ? qy : qz);
       const float diff = qv - __uint_as_float(nd.x);
       const uint32_t right = nd.y >> 2, left = node + 1u;
       const bool go_left = diff < 0.0f;
-      my_stack[sp * kLinBlock] = make_uint2(go_left ? right : left, __float_as_uint(diff * diff));
-      sp++;
+      const float cut = diff * diff;
+      if (cut < best_d) {
+        my_stack[sp * kLinBlock] = make_uint2(go_left ? right : left, __float_as_uint(cut));
+        sp++;
+      }
       node = go_left ? left : right;
       nd = __ldg(&nodes[node]);
       kind = nd.y & 3u;

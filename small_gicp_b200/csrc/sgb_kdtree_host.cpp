@@ -200,4 +200,100 @@ bool build_flat_tree(const float* pts_xyzw, size_t n_points, int max_leaf_size, 
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packet (BVH2) form of a flattened kd-tree: one 64-byte record per INNER node holding the tight bounding boxes and the
+// descriptors of its two children (see sgb_kernels_packet.cu).  Same leaves, same point permutation.
+// ---------------------------------------------------------------------------------------------
+bool build_packet_nodes(const FlatTree& tree, const float* pts_xyzw, std::vector<PacketNode>& out, int* max_pending) {
+  out.clear();
+  *max_pending = 1;
+  const size_t nn = tree.nodes.size();
+  if (nn == 0) return true;
+  struct Box {
+    float lo[3], hi[3];
+  };
+  std::vector<Box> box(nn);
+  std::vector<uint32_t> compact(nn, 0);
+  // children have larger pre-order indices than their parent: one reverse sweep computes every box
+  for (size_t r = nn; r-- > 0;) {
+    const FlatNode nd = tree.nodes[r];
+    Box b;
+    if ((nd.y & 3u) == 3u) {
+      for (int a = 0; a < 3; a++) {
+        b.lo[a] = INFINITY;
+        b.hi[a] = -INFINITY;
+      }
+      const uint32_t first = nd.x, cnt = nd.y >> 2;
+      for (uint32_t j = 0; j < cnt; j++) {
+        const float* p = pts_xyzw + 4 * static_cast<size_t>(tree.perm[first + j]);
+        for (int a = 0; a < 3; a++) {
+          b.lo[a] = std::min(b.lo[a], p[a]);
+          b.hi[a] = std::max(b.hi[a], p[a]);
+        }
+      }
+    } else {
+      const Box &l = box[r + 1], &rr = box[nd.y >> 2];
+      for (int a = 0; a < 3; a++) {
+        b.lo[a] = std::min(l.lo[a], rr.lo[a]);
+        b.hi[a] = std::max(l.hi[a], rr.hi[a]);
+      }
+    }
+    box[r] = b;
+  }
+  uint32_t n_inner = 0;
+  for (size_t i = 0; i < nn; i++)
+    if ((tree.nodes[i].y & 3u) != 3u) compact[i] = n_inner++;
+  auto put_child = [&](PacketNode& pn, int side, size_t child) {
+    const FlatNode c = tree.nodes[child];
+    uint32_t a, b;
+    if ((c.y & 3u) == 3u) {
+      a = c.x;
+      b = c.y >> 2;
+    } else {
+      a = compact[child];
+      b = 0u;
+    }
+    float* v = pn.v + side * 8;
+    for (int k = 0; k < 3; k++) {
+      v[k] = box[child].lo[k];
+      v[4 + k] = box[child].hi[k];
+    }
+    std::memcpy(&v[3], &a, 4);
+    std::memcpy(&v[7], &b, 4);
+    if ((c.y & 3u) == 3u && b == 0u) {  // empty leaf: never wanted
+      for (int k = 0; k < 3; k++) {
+        v[k] = INFINITY;
+        v[4 + k] = -INFINITY;
+      }
+    }
+  };
+  auto put_empty = [](PacketNode& pn, int side) {
+    float* v = pn.v + side * 8;
+    for (int k = 0; k < 3; k++) {
+      v[k] = INFINITY;
+      v[4 + k] = -INFINITY;
+    }
+    const uint32_t z = 0u;
+    std::memcpy(&v[3], &z, 4);
+    std::memcpy(&v[7], &z, 4);
+  };
+  if (n_inner == 0) {  // the whole tree is one leaf: a root whose only child is that leaf
+    out.resize(1);
+    put_child(out[0], 0, 0);
+    put_empty(out[0], 1);
+    if ((tree.nodes[0].y >> 2) == 0u) put_empty(out[0], 0);
+    return true;
+  }
+  out.resize(n_inner);
+  for (size_t i = 0; i < nn; i++) {
+    const FlatNode nd = tree.nodes[i];
+    if ((nd.y & 3u) == 3u) continue;
+    PacketNode& pn = out[compact[i]];
+    put_child(pn, 0, i + 1);
+    put_child(pn, 1, nd.y >> 2);
+  }
+  *max_pending = tree.depth > 0 ? tree.depth : 1;
+  return true;
+}
+
 }  // namespace sgb

@@ -28,32 +28,74 @@ __global__ void __launch_bounds__(kLinBlock) linearize_kd_kernel(const __grid_co
   const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
   const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
 
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
-    const float4 sp = __ldg(&P.src.pts[i]);
-    const double sx = sp.x, sy = sp.y, sz = sp.z;
-    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
-    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
-    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+  // Work unit = chunk of 32*K source positions per warp; lane l handles positions base + k*32 + l, k = 0..K-1,
+  // which are K consecutive points along the Morton curve: the previous result of the lane is a tight search
+  // seed for the next query, and so is the previous linearize's correspondence of the same point.
+  const uint32_t K = P.src.run, chunk_pts = 32u * K;
+  const uint32_t n_chunks = (P.src.n + chunk_pts - 1) / chunk_pts;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+    uint32_t chain = kNone;
+    for (uint32_t k = 0; k < K; k++) {
+      const uint32_t i = chunk * chunk_pts + k * 32u + lane;
+      if (i >= P.src.n) break;
+      const float4 sp = __ldg(&P.src.pts[i]);
+      const double sx = sp.x, sy = sp.y, sz = sp.z;
+      const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
+      const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
+      const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+      const float fx = static_cast<float>(qx), fy = static_cast<float>(qy), fz = static_cast<float>(qz);
 
-    float best_d = P.max_dist_sq;
-    const uint32_t best = kd_nearest(P.tgt.nodes, P.tgt.pts, static_cast<float>(qx), static_cast<float>(qy), static_cast<float>(qz), best_d, s_stack);
-    P.corr[i] = best;
-    if (best == kNone) continue;
+      float best_d = P.max_dist_sq;
+      uint32_t best = kNone;
+      {  // seeds
+        const uint32_t prev = P.use_prev ? P.corr[i] : kNone;
+        if (prev != kNone) {
+          const float4 t = __ldg(&P.tgt.pts[prev]);
+          const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = prev;
+          }
+        }
+        if (chain != kNone && chain != prev) {
+          const float4 t = __ldg(&P.tgt.pts[chain]);
+          const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = chain;
+          }
+        }
+      }
+      best = kd_nearest(P.tgt.nodes, P.tgt.pts, fx, fy, fz, best_d, best, s_stack);
+      if (best != kNone) chain = best;
 
-    const float4 tq = __ldg(&P.tgt.pts[best]);
-    const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
-    Sym3 M;
-    if (FACTOR == 0) {
-      M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
-    } else if (FACTOR == 1) {
-      const float4 n = __ldg(&P.tgt.normals[best]);
-      M = Sym3{static_cast<double>(n.x) * n.x, 0.0, 0.0, static_cast<double>(n.y) * n.y, 0.0, static_cast<double>(n.z) * n.z};
-    } else {
-      M = gicp_precision(R, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[best]), __ldg(&P.tgt.covB[best]));
+      double rx = 0.0, ry = 0.0, rz = 0.0;
+      if (best != kNone) {
+        const float4 tq = __ldg(&P.tgt.pts[best]);
+        rx = static_cast<double>(tq.x) - qx;
+        ry = static_cast<double>(tq.y) - qy;
+        rz = static_cast<double>(tq.z) - qz;
+        if (rx * rx + ry * ry + rz * rz > P.max_dist_sq_d) best = kNone;  // DistanceRejector on the FP64 residual (rejector.hpp:24)
+      }
+      P.corr[i] = best;
+      if (best == kNone) continue;
+
+      Sym3 M;
+      if (FACTOR == 0) {
+        M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+      } else if (FACTOR == 1) {
+        const float4 n = __ldg(&P.tgt.normals[best]);
+        M = Sym3{static_cast<double>(n.x) * n.x, 0.0, 0.0, static_cast<double>(n.y) * n.y, 0.0, static_cast<double>(n.z) * n.z};
+      } else {
+        M = gicp_precision(R, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[best]), __ldg(&P.tgt.covB[best]));
+      }
+      accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
+      acc[kAcc] += 1.0;
     }
-    accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
-    acc[kAcc] += 1.0;
   }
   block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
 }
@@ -85,7 +127,7 @@ __global__ void __launch_bounds__(kLinBlock) linearize_vox_kernel(const __grid_c
   const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - ctx;
   const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - cty;
   const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - ctz;
-  const double max_d = P.max_dist_sq >= FLT_MAX ? DBL_MAX : static_cast<double>(P.max_dist_sq);
+  const double max_d = P.max_dist_sq_d;
 
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
@@ -358,6 +400,17 @@ __global__ void gather_kernel(const uint32_t* __restrict__ perm, size_t n, const
   }
 }
 
+// Morton-rank order -> chunk-transposed order (see LinParams / DevSource::run): out[p] = in[rank(p)]
+__global__ void chunk_transpose_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t K) {
+  const size_t chunk_pts = 32ull * K;
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < n; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t chunk = p / chunk_pts, r = p % chunk_pts;
+    size_t m = p;
+    if ((chunk + 1) * chunk_pts <= n) m = chunk * chunk_pts + (r % 32) * K + r / 32;  // full chunks only; the ragged tail keeps Morton order
+    out[p] = in[m];
+  }
+}
+
 // correspondences in the caller's order: out[perm[i]] = original target index (or voxel id << 32)
 __global__ void correspondences_kernel(const uint32_t* __restrict__ corr, const uint32_t* __restrict__ perm, size_t n, const float4* __restrict__ tgt_pts,
                                        int voxel, uint64_t* out) {
@@ -402,6 +455,12 @@ cudaError_t launch_correspondences(const uint32_t* corr, const uint32_t* perm, s
                                    cudaStream_t st) {
   if (!n) return cudaSuccess;
   correspondences_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(corr, perm, n, tgt_pts, voxel, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_transpose(const uint32_t* in, uint32_t* out, size_t n, uint32_t K, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  chunk_transpose_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(in, out, n, K);
   return cudaGetLastError();
 }
 

@@ -11,6 +11,10 @@ namespace sgb {
 cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool voxel, int grid, int stack_depth, cudaStream_t st);
 cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
 int linearize_occupancy(int stack_depth);
+// sgb_kernels_split.cu
+int search_occupancy(int stack_depth);
+cudaError_t launch_search(const LinParams& P, int grid, int stack_depth, cudaStream_t st);
+cudaError_t launch_factor_reduce(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
 
 cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bounds6, double* d_centre4, int sm_count, cudaStream_t st);
 cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,
@@ -19,7 +23,20 @@ cudaError_t launch_gather(const uint32_t* perm, size_t n, const float4* in0, flo
                           const float4* in3, float4* out3, int sm_count, cudaStream_t st);
 cudaError_t launch_correspondences(const uint32_t* corr, const uint32_t* perm, size_t n, const float4* tgt_pts, int voxel, uint64_t* out, int sm_count,
                                    cudaStream_t st);
+cudaError_t launch_chunk_transpose(const uint32_t* in, uint32_t* out, size_t n, uint32_t K, int sm_count, cudaStream_t st);
 cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                                size_t n, cudaStream_t st);
+
+// sgb_kernels_packet.cu
+int packet_occupancy(int max_depth);
+cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, cudaStream_t st);
+// sgb_preprocess.cu
+cudaError_t launch_features(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
+                            float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st);
+cudaError_t launch_voxel_keys(const double* d_pts4, size_t n, double inv_leaf, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);
+cudaError_t launch_voxel_heads(const uint64_t* keys, size_t n, uint32_t* heads, int sm_count, cudaStream_t st);
+cudaError_t launch_voxel_means(const uint64_t* keys, const uint32_t* vals, const uint32_t* heads, const uint32_t* slots, size_t n, const double* d_pts4,
+                               double* d_out4, int sm_count, cudaStream_t st);
+cudaError_t exclusive_sum_u32(void* d_temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
 
 }  // namespace sgb

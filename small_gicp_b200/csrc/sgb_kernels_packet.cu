@@ -1,0 +1,164 @@
+// SPDX-License-Identifier: MIT
+// Warp-cooperative ("packet") exact nearest-neighbour search -- the search phase of linearize.
+//
+// A warp owns 32 CONSECUTIVE source points of the Morton order, i.e. 32 queries that sit within a small patch of the
+// surface.  Instead of 32 divergent per-thread walks (profiles/r01: 10-14 of 32 lanes active, every lane issuing its own
+// node and point loads), the warp walks the tree ONCE with a single shared traversal stack:
+//   * every control-flow decision is a warp vote, so the instruction stream never diverges;
+//   * node and leaf-point addresses are warp-uniform: one 64 B node / one 16 B point is fetched per warp and broadcast;
+//   * each lane keeps only its own query, best distance and best index; a subtree is entered when ANY lane's search
+//     ball reaches its bounding box, and every lane tests every point of an entered leaf (a superset of what it would
+//     test alone -- the result is still its exact nearest neighbour).
+// The tree is the kd-tree (same leaves, same permutation) with each inner node carrying the tight bounding boxes of its two
+// children (64 B, "BVH2" layout):  float4[4] = {L.lo|L.a, L.hi|L.b, R.lo|R.a, R.hi|R.b} where a child is a leaf
+// (a = first point, b = count > 0) or an inner node (a = node index, b = 0).
+#include <cfloat>
+
+#include "sgb_device.cuh"
+#include "sgb_kernels.h"
+
+namespace sgb {
+
+constexpr int kPktWarps = kLinBlock / 32;
+
+__device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
+  const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+  const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+  const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth) {
+  extern __shared__ float s_dist[];  // [max_depth][kLinBlock] per-lane box distance of each pending subtree
+  __shared__ uint2 s_child[kPktWarps][40];  // per-warp: the pending subtrees themselves (warp-uniform)
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
+  const float4* __restrict__ pts = P.tgt.pts;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_chunks = (P.src.n + 31u) >> 5;
+  float* my_dist = s_dist + threadIdx.x;
+  uint2* my_child = s_child[wib];
+
+  for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+    const uint32_t i = chunk * 32u + lane;
+    const bool valid = i < P.src.n;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    float best_d = -1.0f;  // an idle lane is never interested in anything
+    uint32_t best = kNone;
+    if (valid) {
+      const float4 s = __ldg(&P.src.pts[i]);
+      const double sx = s.x, sy = s.y, sz = s.z;
+      fx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
+      fy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
+      fz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
+      best_d = P.max_dist_sq;
+      const uint32_t prev = P.use_prev ? P.corr[i] : kNone;  // seed: an upper bound only prunes
+      if (prev != kNone) {
+        const float4 t = __ldg(&pts[prev]);
+        const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best_d) {
+          best_d = d;
+          best = prev;
+        }
+      }
+    }
+
+    int sp = 0;
+    uint32_t cur = 0;      // inner node being expanded
+    bool expand = true;    // false: nothing to expand, take the next pending subtree
+    uint32_t leaf_first = 0, leaf_cnt = 0;
+    for (;;) {
+      if (expand) {
+        const float4 n0 = __ldg(&pnodes[cur * 4 + 0]), n1 = __ldg(&pnodes[cur * 4 + 1]);
+        const float4 n2 = __ldg(&pnodes[cur * 4 + 2]), n3 = __ldg(&pnodes[cur * 4 + 3]);
+        const float dl = box_dist2(fx, fy, fz, n0, n1), dr = box_dist2(fx, fy, fz, n2, n3);
+        const bool wl = dl < best_d, wr = dr < best_d;
+        const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+        uint32_t ca, cb;  // descriptor of the child to enter now
+        if (ml && mr) {
+          // enter the child most interested lanes are closer to, keep the other pending
+          const unsigned closer_l = __ballot_sync(0xffffffffu, (wl || wr) && dl <= dr);
+          const bool left_first = 2 * __popc(closer_l) >= __popc(ml | mr);
+          my_dist[sp * kLinBlock] = left_first ? dr : dl;
+          if (lane == 0) my_child[sp] = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
+          sp++;
+          ca = left_first ? __float_as_uint(n0.w) : __float_as_uint(n2.w);
+          cb = left_first ? __float_as_uint(n1.w) : __float_as_uint(n3.w);
+        } else if (ml) {
+          ca = __float_as_uint(n0.w);
+          cb = __float_as_uint(n1.w);
+        } else if (mr) {
+          ca = __float_as_uint(n2.w);
+          cb = __float_as_uint(n3.w);
+        } else {
+          expand = false;
+          continue;
+        }
+        if (cb == 0u) {  // inner child
+          cur = ca;
+          continue;
+        }
+        leaf_first = ca;
+        leaf_cnt = cb;
+      } else {
+        // next pending subtree some lane still cares about
+        bool got = false;
+        uint2 c = make_uint2(0u, 0u);
+        while (sp > 0) {
+          sp--;
+          const float d = my_dist[sp * kLinBlock];
+          if (__any_sync(0xffffffffu, d < best_d)) {
+            __syncwarp();
+            c = my_child[sp];
+            got = true;
+            break;
+          }
+        }
+        if (!got) break;
+        if (c.y == 0u) {
+          cur = c.x;
+          expand = true;
+          continue;
+        }
+        leaf_first = c.x;
+        leaf_cnt = c.y;
+      }
+      // leaf: every lane tests every point (uniform addresses -> one broadcast load per point)
+      const float4* lp = pts + leaf_first;
+#pragma unroll 4
+      for (uint32_t j = 0; j < leaf_cnt; j++) {
+        const float4 t = __ldg(&lp[j]);
+        const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best_d) {
+          best_d = d;
+          best = leaf_first + j;
+        }
+      }
+      expand = false;
+    }
+    __syncwarp();
+    if (valid) P.corr[i] = best;
+  }
+}
+
+int packet_occupancy(int max_depth) {
+  int nb = 0;
+  const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel, kLinBlock, smem) != cudaSuccess) return 1;
+  return nb > 0 ? nb : 1;
+}
+
+cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, cudaStream_t st) {
+  if (max_depth > 40) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
+  packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth);
+  return cudaGetLastError();
+}
+
+}  // namespace sgb

@@ -1,0 +1,321 @@
+// SPDX-License-Identifier: MIT
+// Per-cloud preparation on the device:
+//   * k-nearest-neighbour search of every cloud point in its own kd-tree + local covariance + closed-form 3x3
+//     symmetric eigen-decomposition -> normal and regularised covariance
+//       replaces estimate_normals / estimate_covariances / estimate_normals_covariances{,_omp,_tbb}
+//       (/root/reference/include/small_gicp/util/normal_estimation.hpp:12-140, normal_estimation_omp.hpp:9-60)
+//   * voxel-grid down-sampling: 3 x 21-bit voxel key, radix sort, segmented mean
+//       replaces voxelgrid_sampling{,_omp,_tbb} (.../util/downsampling.hpp:22-78)
+#include <cfloat>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "sgb_device.cuh"
+#include "sgb_kernels.h"
+
+namespace sgb {
+
+// ---------------------------------------------------------------------------------------------
+// k-NN with a register-resident sorted candidate list (ann/knn_result.hpp:80-101 semantics: only strictly
+// closer candidates enter, equal distances keep their arrival order).
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+struct KnnList {
+  float d[KMAX];
+  uint32_t i[KMAX];
+  float worst;
+  int k;
+  __device__ __forceinline__ void init(int k_) {
+    k = k_;
+#pragma unroll
+    for (int j = 0; j < KMAX; j++) {
+      d[j] = FLT_MAX;
+      i[j] = kNone;
+    }
+    worst = FLT_MAX;
+  }
+  __device__ __forceinline__ void offer(float v, uint32_t vi) {
+    if (!(v < worst)) return;
+#pragma unroll
+    for (int j = 0; j < KMAX; j++) {
+      if (j < k && v < d[j]) {
+        const float td = d[j];
+        const uint32_t ti = i[j];
+        d[j] = v;
+        i[j] = vi;
+        v = td;
+        vi = ti;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KMAX; j++)
+      if (j == k - 1) worst = d[j];
+  }
+};
+
+template <int KMAX>
+__device__ __forceinline__ void kd_knn(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, float qx, float qy, float qz, KnnList<KMAX>& L,
+                                       uint2* stack) {
+  uint32_t node = 0;
+  int sp = 0;
+  uint2* my_stack = stack + threadIdx.x;
+  for (;;) {
+    KdNode nd = __ldg(&nodes[node]);
+    uint32_t kind = nd.y & 3u;
+    while (kind != 3u) {
+      const float qv = kind == 0u ? qx : (kind == 1u ? qy : qz);
+      const float diff = qv - __uint_as_float(nd.x);
+      const uint32_t right = nd.y >> 2, left = node + 1u;
+      const bool go_left = diff < 0.0f;
+      const float cut = diff * diff;
+      if (cut < L.worst) {
+        my_stack[sp * kLinBlock] = make_uint2(go_left ? right : left, __float_as_uint(cut));
+        sp++;
+      }
+      node = go_left ? left : right;
+      nd = __ldg(&nodes[node]);
+      kind = nd.y & 3u;
+    }
+    const uint32_t first = nd.x, cnt = nd.y >> 2;
+    for (uint32_t j = 0; j < cnt; j++) {
+      const float4 t = __ldg(&pts[first + j]);
+      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+      L.offer(dx * dx + dy * dy + dz * dz, first + j);
+    }
+    bool found = false;
+    while (sp > 0) {
+      sp--;
+      const uint2 e = my_stack[sp * kLinBlock];
+      if (__uint_as_float(e.y) < L.worst) {  // worst_distance() > cut_sq_dist, ann/kdtree.hpp:228
+        node = e.x;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+}
+
+// Eigenvector of the smallest eigenvalue of a symmetric 3x3 (closed-form roots of the characteristic polynomial,
+// eigenvector from the best-conditioned cross product of two rows of A - lambda I): the only part of the
+// decomposition the regularised covariance and the normal need (normal_estimation.hpp:17-24,40-45).
+__device__ __forceinline__ void smallest_eigenvector(double a00, double a01, double a02, double a11, double a12, double a22, double v[3]) {
+  // shift + scale for conditioning
+  const double shift = (a00 + a11 + a22) / 3.0;
+  double b00 = a00 - shift, b11 = a11 - shift, b22 = a22 - shift, b01 = a01, b02 = a02, b12 = a12;
+  double scale = fmax(fmax(fabs(b00), fabs(b11)), fmax(fabs(b22), fmax(fabs(b01), fmax(fabs(b02), fabs(b12)))));
+  if (!(scale > 0.0)) {
+    v[0] = 1.0;
+    v[1] = 0.0;
+    v[2] = 0.0;
+    return;
+  }
+  const double is = 1.0 / scale;
+  b00 *= is; b11 *= is; b22 *= is; b01 *= is; b02 *= is; b12 *= is;
+  // trace(B) = 0: characteristic polynomial  x^3 - c1' x - det = 0
+  const double p2 = (b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * (b01 * b01 + b02 * b02 + b12 * b12)) / 6.0;  // = (sum eig^2)/6
+  const double det = b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02);
+  const double p = sqrt(p2);
+  double lam_min;
+  if (!(p > 0.0)) {
+    lam_min = 0.0;
+  } else {
+    double r = det / (2.0 * p * p * p);
+    r = fmin(fmax(r, -1.0), 1.0);
+    const double phi = acos(r) / 3.0;
+    // eigenvalues 2p cos(phi + 2 pi k / 3); the smallest is k = 1
+    lam_min = 2.0 * p * cos(phi + 2.0943951023931953);
+  }
+  // rows of C = B - lam_min I ; kernel = cross product of the two most independent rows
+  const double c00 = b00 - lam_min, c11 = b11 - lam_min, c22 = b22 - lam_min;
+  const double r0[3] = {c00, b01, b02}, r1[3] = {b01, c11, b12}, r2[3] = {b02, b12, c22};
+  double x01[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  double x02[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  double x12[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  const double n01 = x01[0] * x01[0] + x01[1] * x01[1] + x01[2] * x01[2];
+  const double n02 = x02[0] * x02[0] + x02[1] * x02[1] + x02[2] * x02[2];
+  const double n12 = x12[0] * x12[0] + x12[1] * x12[1] + x12[2] * x12[2];
+  const double* best = x01;
+  double nb = n01;
+  if (n02 > nb) {
+    best = x02;
+    nb = n02;
+  }
+  if (n12 > nb) {
+    best = x12;
+    nb = n12;
+  }
+  if (!(nb > 1e-280)) {  // (numerically) isotropic: any direction is an eigenvector
+    v[0] = 1.0;
+    v[1] = 0.0;
+    v[2] = 0.0;
+    return;
+  }
+  const double inv = rsqrt(nb);
+  v[0] = best[0] * inv;
+  v[1] = best[1] * inv;
+  v[2] = best[2] * inv;
+}
+
+/// One thread per point of the cloud in LEAF order (neighbouring threads query neighbouring points).
+/// mode bit 0: normals, bit 1: covariances.  Outputs are written in the cloud's ORIGINAL order
+/// (index carried in pts[].w): device layout (float4 streams) and / or the reference's double layout.
+template <int KMAX>
+__global__ void __launch_bounds__(kLinBlock) features_kernel(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, uint32_t n, int k,
+                                                             const double* __restrict__ centre, int mode, float4* out_normals, float4* out_covA,
+                                                             float4* out_covB, double* out_normals_d, double* out_covs_d, int leaf_order_out) {
+  extern __shared__ uint2 s_stack[];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = __ldg(&pts[i]);
+  KnnList<KMAX> L;
+  L.init(k);
+  kd_knn<KMAX>(nodes, pts, q.x, q.y, q.z, L, s_stack);
+  int found = 0;
+  // sums relative to the query point (covariance is translation invariant; keeps the FP64 sums well conditioned)
+  double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < KMAX; j++) {
+    if (j < k && L.i[j] != kNone) {
+      const float4 t = __ldg(&pts[L.i[j]]);
+      const double x = static_cast<double>(t.x) - q.x, y = static_cast<double>(t.y) - q.y, z = static_cast<double>(t.z) - q.z;
+      s[0] += x; s[1] += y; s[2] += z;
+      ss[0] += x * x; ss[1] += x * y; ss[2] += x * z; ss[3] += y * y; ss[4] += y * z; ss[5] += z * z;
+      found++;
+    }
+  }
+  const uint32_t orig = leaf_order_out ? i : static_cast<uint32_t>(__float_as_int(q.w));
+  double nrm[3] = {0.0, 0.0, 0.0};
+  double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};  // < 5 neighbours: identity covariance, zero normal (normal_estimation.hpp:33-37,71-75)
+  if (found >= 5) {
+    const double inv_n = 1.0 / found;
+    const double mx = s[0] * inv_n, my = s[1] * inv_n, mz = s[2] * inv_n;
+    // cov = (sum_cross - mean * sum^T) / n   (normal_estimation.hpp:85-86)
+    const double c00 = (ss[0] - mx * s[0]) * inv_n, c01 = (ss[1] - mx * s[1]) * inv_n, c02 = (ss[2] - mx * s[2]) * inv_n;
+    const double c11 = (ss[3] - my * s[1]) * inv_n, c12 = (ss[4] - my * s[2]) * inv_n, c22 = (ss[5] - mz * s[2]) * inv_n;
+    double v[3];
+    smallest_eigenvector(c00, c01, c02, c11, c12, c22, v);
+    // V diag(1e-3, 1, 1) V^T = I - (1 - 1e-3) v v^T for orthonormal V
+    const double w = 1.0 - 1e-3;
+    cov[0] = 1.0 - w * v[0] * v[0]; cov[1] = -w * v[0] * v[1]; cov[2] = -w * v[0] * v[2];
+    cov[3] = 1.0 - w * v[1] * v[1]; cov[4] = -w * v[1] * v[2]; cov[5] = 1.0 - w * v[2] * v[2];
+    // flip the normal toward the origin of the cloud's own frame (normal_estimation.hpp:19-23)
+    const double px = static_cast<double>(q.x) + centre[0], py = static_cast<double>(q.y) + centre[1], pz = static_cast<double>(q.z) + centre[2];
+    const double sgn = (px * v[0] + py * v[1] + pz * v[2]) > 0.0 ? -1.0 : 1.0;
+    nrm[0] = sgn * v[0]; nrm[1] = sgn * v[1]; nrm[2] = sgn * v[2];
+  }
+  if (mode & 1) {
+    if (out_normals) out_normals[orig] = make_float4((float)nrm[0], (float)nrm[1], (float)nrm[2], 0.f);
+    if (out_normals_d) {
+      double* o = out_normals_d + static_cast<size_t>(orig) * 4;
+      o[0] = nrm[0]; o[1] = nrm[1]; o[2] = nrm[2]; o[3] = 0.0;
+    }
+  }
+  if (mode & 2) {
+    if (out_covA) {
+      out_covA[orig] = make_float4((float)cov[0], (float)cov[1], (float)cov[2], (float)cov[3]);
+      out_covB[orig] = make_float4((float)cov[4], (float)cov[5], 0.f, 0.f);
+    }
+    if (out_covs_d) {
+      double* o = out_covs_d + static_cast<size_t>(orig) * 16;
+      o[0] = cov[0]; o[1] = cov[1]; o[2] = cov[2]; o[3] = 0.0;
+      o[4] = cov[1]; o[5] = cov[3]; o[6] = cov[4]; o[7] = 0.0;
+      o[8] = cov[2]; o[9] = cov[4]; o[10] = cov[5]; o[11] = 0.0;
+      o[12] = 0.0; o[13] = 0.0; o[14] = 0.0; o[15] = 0.0;
+    }
+  }
+}
+
+template <int KMAX>
+static cudaError_t launch_features_t(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* on, float4* oa, float4* ob,
+                                     double* ond, double* ocd, int depth, int leaf_order_out, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(depth > 0 ? depth : 1) * kLinBlock * sizeof(uint2);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(features_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = static_cast<int>((n + kLinBlock - 1) / kLinBlock);
+  features_kernel<KMAX><<<grid, kLinBlock, smem, st>>>(nodes, pts, n, k, centre, mode, on, oa, ob, ond, ocd, leaf_order_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_features(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
+                            float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (k <= 10) return launch_features_t<10>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
+  if (k <= 20) return launch_features_t<20>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
+  if (k <= 32) return launch_features_t<32>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
+  return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
+// voxel-grid down-sampling
+// ---------------------------------------------------------------------------------------------
+__global__ void voxel_keys_kernel(const double4* __restrict__ pts, size_t n, double inv_leaf, uint64_t* keys, uint32_t* vals) {
+  constexpr int coord_bit_size = 21;
+  constexpr int64_t coord_bit_mask = (1 << 21) - 1;
+  constexpr int coord_offset = 1 << (coord_bit_size - 1);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double4 p = pts[i];
+    const int64_t cx = static_cast<int64_t>(floor(p.x * inv_leaf)) + coord_offset;
+    const int64_t cy = static_cast<int64_t>(floor(p.y * inv_leaf)) + coord_offset;
+    const int64_t cz = static_cast<int64_t>(floor(p.z * inv_leaf)) + coord_offset;
+    uint64_t key = ~0ull;  // out of the 21-bit range: dropped (downsampling.hpp:41-45 warns and marks them invalid)
+    if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= coord_bit_mask && cy <= coord_bit_mask && cz <= coord_bit_mask)
+      key = static_cast<uint64_t>(cx) | (static_cast<uint64_t>(cy) << coord_bit_size) | (static_cast<uint64_t>(cz) << (2 * coord_bit_size));
+    keys[i] = key;
+    vals[i] = static_cast<uint32_t>(i);
+  }
+}
+
+__global__ void voxel_heads_kernel(const uint64_t* __restrict__ keys, size_t n, uint32_t* heads) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint64_t k = keys[i];
+    heads[i] = (k != ~0ull && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+  }
+}
+
+// one thread per segment head: mean of the segment's points in sorted (= original index) order, FP64
+__global__ void voxel_means_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ heads,
+                                   const uint32_t* __restrict__ slots, size_t n, const double4* __restrict__ pts, double4* out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (!heads[i]) continue;
+    const uint64_t k = keys[i];
+    double sx = 0, sy = 0, sz = 0, cnt = 0;
+    for (size_t j = i; j < n && keys[j] == k; j++) {
+      const double4 p = pts[vals[j]];
+      sx += p.x; sy += p.y; sz += p.z; cnt += 1.0;
+    }
+    out[slots[i]] = make_double4(sx / cnt, sy / cnt, sz / cnt, 1.0);
+  }
+}
+
+static int vgrid(size_t n, int cap) {
+  size_t g = (n + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  return static_cast<int>(g);
+}
+
+cudaError_t launch_voxel_keys(const double* d_pts4, size_t n, double inv_leaf, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  voxel_keys_kernel<<<vgrid(n, sm_count * 8), 256, 0, st>>>(reinterpret_cast<const double4*>(d_pts4), n, inv_leaf, keys, vals);
+  return cudaGetLastError();
+}
+cudaError_t launch_voxel_heads(const uint64_t* keys, size_t n, uint32_t* heads, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  voxel_heads_kernel<<<vgrid(n, sm_count * 8), 256, 0, st>>>(keys, n, heads);
+  return cudaGetLastError();
+}
+cudaError_t launch_voxel_means(const uint64_t* keys, const uint32_t* vals, const uint32_t* heads, const uint32_t* slots, size_t n, const double* d_pts4,
+                               double* d_out4, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  voxel_means_kernel<<<vgrid(n, sm_count * 8), 256, 0, st>>>(keys, vals, heads, slots, n, reinterpret_cast<const double4*>(d_pts4),
+                                                             reinterpret_cast<double4*>(d_out4));
+  return cudaGetLastError();
+}
+cudaError_t exclusive_sum_u32(void* d_temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
+  return cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, out, static_cast<int>(n), st);
+}
+
+}  // namespace sgb

@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, source points sharded in contiguous
+ranges, target + search structure replicated, ONE all-reduce(sum) of H|b|e|num_inliers (44 doubles) per linearize and
+of e (1 double) per error.  All ranks then solve the same 6x6 system, so no broadcast of the update is needed.
+
+torch.distributed is the transport (NCCL on GPUs, gloo in the CPU tests); the per-rank reduction is any object with
+linearize_into(T, out44) / error_into(T, out1) writing into a torch tensor (GPU: small_gicp_b200.Context writing
+device memory on the current stream; tests: the CPU oracle)."""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced split of range(n): the first n % world ranks get one extra element."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedReduction:
+    """Reduction::linearize / ::error over a source sharded across the ranks of a process group."""
+
+    def __init__(self, local, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.local = local
+        self.dist = dist
+        self.group = group
+        self.buf = torch.zeros(64, dtype=torch.float64, device=device)
+
+    def linearize(self, T, **kw):
+        """-> (H 6x6, b 6, e, num_inliers) identical on every rank"""
+        self.local.linearize_into(T, self.buf, **kw)
+        if self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+            self.dist.all_reduce(self.buf[:44], op=self.dist.ReduceOp.SUM, group=self.group)
+        h = self.buf[:44].cpu().numpy()
+        return h[:36].reshape(6, 6).copy(), h[36:42].copy(), float(h[42]), int(round(h[43]))
+
+    def error(self, T):
+        self.local.error_into(T, self.buf[48:49])
+        if self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+            self.dist.all_reduce(self.buf[48:49], op=self.dist.ReduceOp.SUM, group=self.group)
+        return float(self.buf[48].cpu())
+
+
+class ContextReduction:
+    """Adapter: a small_gicp_b200.Context whose source holds this rank's shard; writes straight into device memory."""
+
+    def __init__(self, ctx, factor, robust=0, robust_c=1.0, rejector=1, max_dist_sq=1.0):
+        self.ctx, self.kw = ctx, dict(factor=factor, robust=robust, robust_c=robust_c, rejector=rejector, max_dist_sq=max_dist_sq)
+
+    def linearize_into(self, T, buf):
+        self.ctx.linearize_device(T, buf.data_ptr(), **self.kw)
+
+    def error_into(self, T, buf1):
+        self.ctx.error_device(T, buf1.data_ptr())

@@ -1,0 +1,110 @@
+"""Device-side per-cloud preparation against the oracle's restatement of
+util/downsampling.hpp:22-78 and util/normal_estimation.hpp:12-140."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import small_gicp_b200 as sg
+
+    c = sg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("leaf", [0.1, 0.25, 0.5, 1.0])
+def test_voxelgrid_matches_oracle(golden, ctx, leaf):
+    tgt, src, _ = golden
+    for xyz in (tgt, src):
+        ref = O.Cloud(xyz).voxelgrid_sampling(leaf).points
+        got = ctx.voxelgrid_sampling(xyz, leaf)
+        assert got.shape == ref.shape  # downsampling_test.cpp:90-98 compares sizes; we require equality
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)  # same voxel order (ascending key), same means
+        assert np.all(got[:, 3] == 1.0)
+
+
+def test_voxelgrid_edge_cases(ctx):
+    assert ctx.voxelgrid_sampling(np.zeros((0, 3)), 0.25).shape == (0, 4)
+    one = ctx.voxelgrid_sampling(np.array([[1.0, 2.0, 3.0]]), 0.25)
+    np.testing.assert_allclose(one, [[1.0, 2.0, 3.0, 1.0]])
+    # negative coordinates use floor, not truncation (fast_floor.hpp:12-15)
+    pts = np.array([[-0.1, -0.1, -0.1], [-0.2, -0.2, -0.2], [0.1, 0.1, 0.1]])
+    got = ctx.voxelgrid_sampling(pts, 1.0)
+    ref = O.Cloud(pts).voxelgrid_sampling(1.0).points
+    np.testing.assert_allclose(got, ref, atol=1e-12)
+    # out-of-range voxel coordinates are dropped
+    far = np.array([[0.0, 0.0, 0.0], [1e9, 0.0, 0.0]])
+    assert len(ctx.voxelgrid_sampling(far, 0.25)) == 1
+
+
+@pytest.mark.parametrize("k", [10, 20])
+def test_features_match_oracle(golden, ctx, k):
+    tgt, _, _ = golden
+    cloud = O.Cloud(tgt).voxelgrid_sampling(0.25)
+    tree = O.KdTree(cloud)
+    tree.estimate(k, O.FEAT_NORMAL_COV, max(1, O.max_threads()))
+    P, N0, C0 = cloud.points, cloud.normals, cloud.covs
+    N, C = ctx.estimate_features(P, k)
+    # structural properties (normal_estimation_test.cpp:39-77)
+    np.testing.assert_allclose(np.linalg.norm(N[:, :3], axis=1), 1.0, atol=1e-9)
+    assert np.all(N[:, 3] == 0) and np.all(C[:, 3, :] == 0) and np.all(C[:, :, 3] == 0)
+    np.testing.assert_allclose(C, np.swapaxes(C, 1, 2), atol=1e-15)
+    assert np.all(np.einsum("ij,ij->i", P[:, :3], N[:, :3]) <= 1e-9)
+    # values: identical neighbour sets give the same eigenvector up to rounding; FP32 near-ties at the k-th neighbour
+    # may swap one neighbour for a few points
+    # the orientation test (p . n > 0 -> flip) is a coin toss when p . n ~ 0: compare normals up to sign, and require
+    # every sign disagreement to sit on that boundary
+    flipped = np.einsum("ij,ij->i", N[:, :3], N0[:, :3]) < 0
+    pn = np.abs(np.einsum("ij,ij->i", P[:, :3], N0[:, :3])) / np.linalg.norm(P[:, :3], axis=1)
+    assert flipped.sum() <= 5 and np.all(pn[flipped] < 1e-3)
+    dn = np.minimum(np.abs(N - N0).max(axis=1), np.abs(N + N0).max(axis=1))
+    dc = np.abs(C - C0).reshape(len(P), -1).max(axis=1)
+    ok = (dn < 1e-5) & (dc < 1e-5)
+    assert ok.mean() > 0.995, ok.mean()
+    assert np.median(dn) < 5e-6 and np.median(dc) < 5e-6  # FP32 coordinate storage
+    # the rest: FP32 near-ties at the k-th neighbour swap one neighbour out of k for a few points
+    assert np.quantile(dn, 0.999) < 0.2, np.quantile(dn, 0.999)
+
+
+def test_features_few_points(ctx):
+    pts = np.random.default_rng(0).normal(size=(4, 3))
+    N, C = ctx.estimate_features(pts, 10)
+    assert not N.any()  # < 5 neighbours: zero normal, identity covariance
+    ident = np.eye(4)
+    ident[3, 3] = 0
+    np.testing.assert_allclose(C, np.tile(ident, (4, 1, 1)))
+
+
+def test_device_resident_pipeline(golden):
+    """points only -> tree + features computed on the device -> GICP linearize; equals the path where the same
+    features come back to the host and are uploaded again."""
+    import small_gicp_b200 as sg
+
+    tgt, src, T = golden
+    a, b = sg.Context(0), sg.Context(0)
+    tp = a.voxelgrid_sampling(tgt, 0.25)
+    sp = a.voxelgrid_sampling(src, 0.25)
+    # resident
+    a.set_target(tp)
+    a.build_target_kdtree()
+    a.estimate_target_features(10)
+    a.set_source(sp)
+    a.estimate_source_features(10)
+    # round trip
+    tn, tc = b.estimate_features(tp, 10)
+    _, sc = b.estimate_features(sp, 10, normals=False)
+    b.set_target(tp, tn, tc)
+    b.build_target_kdtree()
+    b.set_source(sp, sc)
+    for factor in (sg.FACTOR_GICP, sg.FACTOR_PLANE_ICP):
+        Ha, ba, ea = a.linearize(T, factor=factor)
+        Hb, bb, eb = b.linearize(T, factor=factor)
+        assert np.linalg.norm(Ha - Hb) <= 1e-4 * np.linalg.norm(Hb) and abs(ea - eb) <= 1e-4 * eb
+        assert np.array_equal(a.correspondences(), b.correspondences())
+    a.close()
+    b.close()
