@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r01e}
+TAG=${1:-r01f}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== pytest -m gpu" | tee $OUT/pytest.log
@@ -15,12 +15,8 @@ except Exception as e:
     print("fail", e); print(open("$1".replace(".json",".err")).read()[-1500:])
 PY
 }
-for mode in 2 1; do for leaf in 20 32 64; do
+for mode in 2 1; do for leaf in 8 12 16; do
   name=m${mode}_l${leaf}
   SGB_SEARCH=$mode timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --leaf $leaf > $OUT/bench_$name.json 2> $OUT/bench_$name.err
   show $OUT/bench_$name.json "mode=$mode leaf=$leaf"
 done; done
-echo "== ncu full capture (packet)"
-SGB_SEARCH=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"packet_search_kernel|factor_reduce_kernel" -s 16 -c 4 -f -o $OUT/prof_packet \
-    python bench.py --steps 4 --warmup 1 --no-cpu-baseline --leaf 32 > $OUT/ncu_full.log 2>&1
-echo "rc=$?"

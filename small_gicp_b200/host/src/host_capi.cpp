@@ -12,6 +12,7 @@
 #include <small_gicp_b200/kdtree.hpp>
 #include <small_gicp_b200/reduction_cuda.hpp>
 #include <small_gicp_b200/registration.hpp>
+#include <small_gicp_b200/registration_helper.hpp>
 #include <small_gicp_b200/voxelmap.hpp>
 
 using namespace small_gicp_b200;
@@ -165,6 +166,50 @@ int sgbh_align(size_t n_target, const double* target_pts4, const double* target_
     scalars_out4[3] = r.error;
     if (H_out36) std::memcpy(H_out36, r.H.data(), sizeof(double) * 36);
     if (b_out6) std::memcpy(b_out6, r.b.data(), sizeof(double) * 6);
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 2;
+  }
+}
+
+/// small_gicp::align(target_points, source_points, init_T, setting) of the helper API (registration_helper.cpp:58-69):
+/// raw points in; settings8 = [type, voxel_resolution, downsampling_resolution, max_correspondence_distance, rotation_eps,
+/// translation_eps, max_iterations, device].  sizes_out2 = down-sampled target / source sizes (informational).
+int sgbh_helper_align(size_t n_target, const double* target_pts4, size_t n_source, const double* source_pts4, const double* settings8, const double* init_T16,
+                      double* T_out16, double* scalars_out4, double* sizes_out2) {
+  try {
+    RegistrationSetting s;
+    s.type = static_cast<RegistrationSetting::RegistrationType>(static_cast<int>(settings8[0]));
+    s.voxel_resolution = settings8[1];
+    s.downsampling_resolution = settings8[2];
+    s.max_correspondence_distance = settings8[3];
+    s.rotation_eps = settings8[4];
+    s.translation_eps = settings8[5];
+    s.max_iterations = static_cast<int>(settings8[6]);
+    s.device = static_cast<int>(settings8[7]);
+    auto target = make_cloud(n_target, target_pts4, nullptr, nullptr);
+    auto source = make_cloud(n_source, source_pts4, nullptr, nullptr);
+    Isometry3d init;
+    std::memcpy(init.matrix().data(), init_T16, sizeof(double) * 16);
+    auto [tp, tt] = preprocess_points(*target, s.downsampling_resolution, 10, s.num_threads, s.device);
+    auto [sp, st] = preprocess_points(*source, s.downsampling_resolution, 10, s.num_threads, s.device);
+    RegistrationResult r;
+    if (s.type == RegistrationSetting::VGICP) {
+      auto vm = create_gaussian_voxelmap(*tp, s.voxel_resolution);
+      r = align(*vm, *sp, init, s);
+    } else {
+      r = align(*tp, *sp, *tt, init, s);
+    }
+    std::memcpy(T_out16, r.T_target_source.matrix().data(), sizeof(double) * 16);
+    scalars_out4[0] = r.converged ? 1.0 : 0.0;
+    scalars_out4[1] = static_cast<double>(r.iterations);
+    scalars_out4[2] = static_cast<double>(r.num_inliers);
+    scalars_out4[3] = r.error;
+    if (sizes_out2) {
+      sizes_out2[0] = static_cast<double>(tp->size());
+      sizes_out2[1] = static_cast<double>(sp->size());
+    }
     return 0;
   } catch (const std::exception& e) {
     g_error = e.what();

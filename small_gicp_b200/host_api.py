@@ -98,6 +98,32 @@ def align(
     return r
 
 
+ICP, PLANE_ICP, GICP, VGICP = 0, 1, 2, 3  # RegistrationSetting::RegistrationType
+
+
+def helper_align(target_points, source_points, init_T=None, type=GICP, voxel_resolution=1.0, downsampling_resolution=0.25, max_correspondence_distance=1.0,
+                 rotation_eps=0.1 * np.pi / 180.0, translation_eps=1e-3, max_iterations=20, device=0):
+    """small_gicp::align(target, source, init_T, RegistrationSetting) on raw points (registration_helper.cpp:58-69):
+    device voxel-grid sampling (0.25 m), k = 10 normals + covariances, kd-tree, LM registration with the CUDA reduction."""
+    L = _lib()
+    if not hasattr(L.sgbh_helper_align, "_typed"):
+        L.sgbh_helper_align.restype = C.c_int
+        L.sgbh_helper_align.argtypes = [C.c_size_t, _dp, C.c_size_t, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.sgbh_helper_align._typed = True
+    tp, sp = capi._points4(target_points), capi._points4(source_points)
+    s = np.array([type, voxel_resolution, downsampling_resolution, max_correspondence_distance, rotation_eps, translation_eps, max_iterations, device], dtype=np.float64)
+    T0 = np.ascontiguousarray((np.eye(4) if init_T is None else np.asarray(init_T, dtype=float)).T)
+    T, sc4, sizes = np.empty(16), np.empty(4), np.empty(2)
+    rc = L.sgbh_helper_align(tp.shape[0], _d(tp), sp.shape[0], _d(sp), _d(s), _d(T0), _d(T), _d(sc4), _d(sizes))
+    if rc != 0:
+        raise capi.SgbError(L.sgbh_last_error().decode())
+    r = Result()
+    r.T_target_source = T.reshape(4, 4).T.copy()
+    r.converged, r.iterations, r.num_inliers, r.error = bool(sc4[0]), int(sc4[1]), int(sc4[2]), float(sc4[3])
+    r.target_size, r.source_size = int(sizes[0]), int(sizes[1])
+    return r
+
+
 def kdtree_knn(points, queries, k):
     """KdTree<PointCloud>(points).knn_search for each query (host mirror, CPU)."""
     L = _lib()

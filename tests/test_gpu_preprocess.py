@@ -61,7 +61,10 @@ def test_features_match_oracle(golden, ctx, k):
     # every sign disagreement to sit on that boundary
     flipped = np.einsum("ij,ij->i", N[:, :3], N0[:, :3]) < 0
     pn = np.abs(np.einsum("ij,ij->i", P[:, :3], N0[:, :3])) / np.linalg.norm(P[:, :3], axis=1)
-    assert flipped.sum() <= 5 and np.all(pn[flipped] < 1e-3)
+    assert flipped.sum() <= 5 and np.all((pn[flipped] < 1e-3) | ~np.isfinite(pn[flipped])), (flipped.sum(), pn[flipped])
+    assert np.isfinite(N0).all(axis=1).mean() > 0.999  # the oracle's closed-form solver may emit NaN on degenerate neighbourhoods
+    N0 = np.nan_to_num(N0)
+    C0 = np.nan_to_num(C0)
     dn = np.minimum(np.abs(N - N0).max(axis=1), np.abs(N + N0).max(axis=1))
     dc = np.abs(C - C0).reshape(len(P), -1).max(axis=1)
     ok = (dn < 1e-5) & (dc < 1e-5)

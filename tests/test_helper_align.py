@@ -1,0 +1,64 @@
+"""BASELINE config 1: bundled data/target.ply <-> data/source.ply through the reference helper `align()` surface
+(registration_helper.cpp:58-137: 0.25 m voxel grid, k = 10 normals + covariances, kd-tree, LM, 20 iterations, 1 m) --
+the C++ host mirror with every stage on the device, against the oracle's restatement of the same pipeline."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import pose_error
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle_pipeline(golden):
+    tgt, src, T = golden
+    tc, tt = O.preprocess_points(tgt, 0.25, 10, 1)
+    sc, st = O.preprocess_points(src, 0.25, 10, 1)
+    return tc, tt, sc, T
+
+
+@pytest.mark.parametrize("name,kind,factor", [("ICP", 0, O.FACTOR_ICP), ("PLANE_ICP", 1, O.FACTOR_PLANE), ("GICP", 2, O.FACTOR_GICP)])
+def test_helper_align_matches_oracle(golden, oracle_pipeline, name, kind, factor):
+    from small_gicp_b200 import host_api
+
+    tgt, src, Tgt = golden
+    tc, tt, sc, _ = oracle_pipeline
+    reg = O.Registration(factor=factor, num_threads=1)  # helper: ParallelReductionOMP(num_threads), LM defaults
+    ref = reg.align(tc, tt, sc, np.eye(4))
+    r = host_api.helper_align(tgt, src, type=kind)
+    assert (r.target_size, r.source_size) == (len(tc), len(sc)) == (6147, 6167)
+    rot, trans = pose_error(Tgt, r.T_target_source)
+    assert rot < np.deg2rad(2.5) and trans < 0.2  # helper_test.cpp:27-39
+    rot, trans = pose_error(ref.T_target_source, r.T_target_source)
+    if kind == 0:
+        # ICP uses points only: identical inputs (device voxel grid == oracle's to 1e-9) -> the north-star bar
+        assert rot < 1e-4 and trans < 1e-3, (rot, trans)
+        assert r.iterations == ref.iterations and abs(r.num_inliers - ref.num_inliers) <= 2
+    else:
+        # normals / covariances come from the device k-NN (FP32 near-ties swap a neighbour for a few points)
+        assert rot < 2e-3 and trans < 1e-2, (name, rot, trans)
+
+
+def test_helper_align_vgicp(golden, oracle_pipeline):
+    from small_gicp_b200 import host_api
+
+    tgt, src, Tgt = golden
+    tc, tt, sc, _ = oracle_pipeline
+    vm = O.GaussianVoxelMap(tc, 1.0)
+    ref = O.Registration(factor=O.FACTOR_GICP, num_threads=1).align(vm, None, sc, np.eye(4))
+    r = host_api.helper_align(tgt, src, type=host_api.VGICP)
+    rot, trans = pose_error(Tgt, r.T_target_source)
+    assert rot < np.deg2rad(2.5) and trans < 0.2
+    rot, trans = pose_error(ref.T_target_source, r.T_target_source)
+    assert rot < 2e-3 and trans < 1e-2, (rot, trans)
+
+
+def test_helper_align_empty(golden):
+    from small_gicp_b200 import host_api
+
+    tgt, src, _ = golden
+    r = host_api.helper_align(np.zeros((0, 3)), src[:1000])
+    assert r.target_size == 0 and r.num_inliers == 0
+    r = host_api.helper_align(tgt[:1000], np.zeros((0, 3)))
+    assert r.source_size == 0 and np.allclose(r.T_target_source, np.eye(4))
