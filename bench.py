@@ -64,8 +64,10 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------------
 # inputs
 # ------------------------------------------------------------------------------------------------
-def make_inputs(points, rank, covs_mode):
-    """target (shared by all ranks) and this rank's source shard; covariances as 4x4 zero-padded doubles."""
+def make_inputs(points, rank, covs_mode, estimator=None):
+    """target (shared by all ranks) and this rank's source shard; covariances as 4x4 zero-padded doubles.
+    covs_mode "knn": the reference recipe (k = 20 neighbours, eigenvalues -> (1e-3, 1, 1), normal_estimation.hpp:28-92)
+    evaluated by `estimator(points4) -> covs` (our arm: the device estimator; reference arm: the oracle's)."""
     from small_gicp_b200 import synthetic as syn
 
     world = syn.make_world(points, 42)
@@ -79,14 +81,13 @@ def make_inputs(points, rank, covs_mode):
     src = src.astype(np.float32).astype(np.float64)
     tgt4 = np.concatenate([tgt, np.ones((len(tgt), 1))], axis=1)
     src4 = np.concatenate([src, np.ones((len(src), 1))], axis=1)
-    return {
-        "target": tgt4,
-        "source": src4,
-        "target_covs": syn.plane_covariances(tn),
-        "source_covs": syn.plane_covariances(sn),
-        "T_gt": Tgt,
-        "covs": "analytic plane covariances I-(1-1e-3)nn^T from the generator's face normals",
-    }
+    if covs_mode == "knn" and estimator is not None:
+        tcov, scov = estimator(tgt4), estimator(src4)
+        desc = "k=20 nearest-neighbour covariances, eigenvalues regularised to (1e-3,1,1) (reference recipe)"
+    else:
+        tcov, scov = syn.plane_covariances(tn), syn.plane_covariances(sn)
+        desc = "analytic plane covariances I-(1-1e-3)nn^T from the generator's face normals"
+    return {"target": tgt4, "source": src4, "target_covs": tcov, "source_covs": scov, "T_gt": Tgt, "covs": desc}
 
 
 def se3_exp(a):
@@ -197,7 +198,14 @@ def run_reference(args):
     import oracle as O
 
     threads = O.max_threads()
-    inp = make_inputs(args.points, 0, args.covs)
+
+    def oracle_covs(p4):  # the reference arm prepares its inputs with the CPU oracle only (none of our kernels on this arm)
+        c = O.Cloud(p4)
+        t = O.KdTree(c)
+        t.estimate(20, O.FEAT_COV, threads)
+        return c.covs
+
+    inp = make_inputs(args.points, 0, args.covs, oracle_covs)
     O, tc, tt, sc, reg, build_s = cpu_setup(inp, threads)
     poses, _ = gn_trajectory(lambda T: reg.linearize(tc, tt, sc, T))
     for i in range(args.warmup):
@@ -271,9 +279,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    inp = make_inputs(args.points, rank, args.covs)
-    n_src = inp["source"].shape[0]
     ctx = sg.Context(local_rank)
+    inp = make_inputs(args.points, rank, args.covs, lambda p4: ctx.estimate_features(p4, 20, normals=False)[1])
+    n_src = inp["source"].shape[0]
     # one explicit (non-default) stream for everything: the context's kernels, torch's fills / events and NCCL all
     # run on it, so CUDA events recorded on it bracket exactly the work being timed
     stream = torch.cuda.Stream(device=dev)

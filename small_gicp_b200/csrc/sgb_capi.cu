@@ -249,6 +249,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   }
   ctx->stream = ctx->own_stream;
   if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
+  if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
   *out_ctx = ctx;
   return 0;
 }

@@ -20,6 +20,9 @@
 namespace sgb {
 
 constexpr int kPktWarps = kLinBlock / 32;
+// a leaf wanted by more lanes than this is scanned by all lanes (10 instr / point); otherwise the interested lanes are
+// served one by one by the whole warp (~16 instr / lane): break-even ~ points_per_leaf * 10 / 16
+constexpr int kPacketDenseLanes = 18;
 
 __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
   const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
     uint32_t cur = 0;      // inner node being expanded
     bool expand = true;    // false: nothing to expand, take the next pending subtree
     uint32_t leaf_first = 0, leaf_cnt = 0;
+    float leaf_d = 0.f;  // this lane's distance to the box of the leaf about to be scanned
     for (;;) {
       if (expand) {
         const float4 n0 = __ldg(&pnodes[cur * 4 + 0]), n1 = __ldg(&pnodes[cur * 4 + 1]);
@@ -89,12 +93,15 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
           sp++;
           ca = left_first ? __float_as_uint(n0.w) : __float_as_uint(n2.w);
           cb = left_first ? __float_as_uint(n1.w) : __float_as_uint(n3.w);
+          leaf_d = left_first ? dl : dr;
         } else if (ml) {
           ca = __float_as_uint(n0.w);
           cb = __float_as_uint(n1.w);
+          leaf_d = dl;
         } else if (mr) {
           ca = __float_as_uint(n2.w);
           cb = __float_as_uint(n3.w);
+          leaf_d = dr;
         } else {
           expand = false;
           continue;
@@ -115,6 +122,7 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
           if (__any_sync(0xffffffffu, d < best_d)) {
             __syncwarp();
             c = my_child[sp];
+            leaf_d = d;
             got = true;
             break;
           }
@@ -128,16 +136,47 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
         leaf_first = c.x;
         leaf_cnt = c.y;
       }
-      // leaf: every lane tests every point (uniform addresses -> one broadcast load per point)
-      const float4* lp = pts + leaf_first;
+      // ---- leaf ----
+      // Only the lanes whose ball reaches this leaf's box need its points; typically a handful of the 32.
+      unsigned want = __ballot_sync(0xffffffffu, leaf_d < best_d);
+      if (__popc(want) > kPacketDenseLanes) {
+        // many interested lanes: every lane tests every point (uniform addresses -> one broadcast load per point)
+        const float4* lp = pts + leaf_first;
 #pragma unroll 4
-      for (uint32_t j = 0; j < leaf_cnt; j++) {
-        const float4 t = __ldg(&lp[j]);
-        const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-        const float d = dx * dx + dy * dy + dz * dz;
-        if (d < best_d) {
-          best_d = d;
-          best = leaf_first + j;
+        for (uint32_t j = 0; j < leaf_cnt; j++) {
+          const float4 t = __ldg(&lp[j]);
+          const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = leaf_first + j;
+          }
+        }
+      } else {
+        // few interested lanes: serve them one at a time with the WHOLE warp -- lane j holds point j of the leaf, the
+        // query is broadcast by shuffle, the nearest point comes out of one hardware min-reduction (squared distances
+        // are non-negative floats, so their bit patterns order like unsigned integers)
+        for (uint32_t base = 0; base < leaf_cnt; base += 32u) {
+          const uint32_t j = base + lane;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < leaf_cnt) t = __ldg(&pts[leaf_first + j]);
+          unsigned todo = want;
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float qx = __shfl_sync(0xffffffffu, fx, src), qy = __shfl_sync(0xffffffffu, fy, src), qz = __shfl_sync(0xffffffffu, fz, src);
+            const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+            const uint32_t dbits = j < leaf_cnt ? __float_as_uint(dx * dx + dy * dy + dz * dz) : 0x7f800000u;
+            const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
+            const unsigned who = __ballot_sync(0xffffffffu, dbits == dmin);  // lowest lane = first point in scan order
+            if (static_cast<int>(lane) == src) {
+              const float d = __uint_as_float(dmin);
+              if (d < best_d) {
+                best_d = d;
+                best = leaf_first + base + (__ffs(who) - 1);
+              }
+            }
+          }
         }
       }
       expand = false;
