@@ -191,13 +191,36 @@ def cpu_setup(inp, threads):
     return O, tc, tt, sc, reg, build_s
 
 
+def host_threads():
+    """All the host threads the CPU path can use.  torchrun exports OMP_NUM_THREADS=1 and torch pins OpenMP to the physical
+    core count, so the count is passed explicitly (the oracle's parallel regions carry a num_threads() clause, like
+    reduction_omp.hpp:36)."""
+    return max(1, os.cpu_count() or 1)
+
+
+def best_cpu_registration(inp):
+    """Time one linearize with all logical CPUs and with half of them (= physical cores on an SMT-2 host) and keep the faster."""
+    best = None
+    n = host_threads()
+    for threads in sorted({n, max(1, n // 2)}, reverse=True):
+        O, tc, tt, sc, reg, build_s = cpu_setup(inp, threads)
+        reg.linearize(tc, tt, sc, np.eye(4))
+        t0 = time.perf_counter()
+        reg.linearize(tc, tt, sc, np.eye(4))
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, threads, (O, tc, tt, sc, reg, build_s))
+    return best[1], best[2]
+
+
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())  # before libgomp is loaded (torchrun sets it to 1)
     import oracle as O
 
-    threads = O.max_threads()
+    threads = host_threads()
 
     def oracle_covs(p4):  # the reference arm prepares its inputs with the CPU oracle only (none of our kernels on this arm)
         c = O.Cloud(p4)
@@ -206,7 +229,7 @@ def run_reference(args):
         return c.covs
 
     inp = make_inputs(args.points, 0, args.covs, oracle_covs)
-    O, tc, tt, sc, reg, build_s = cpu_setup(inp, threads)
+    threads, (O, tc, tt, sc, reg, build_s) = best_cpu_registration(inp)
     poses, _ = gn_trajectory(lambda T: reg.linearize(tc, tt, sc, T))
     for i in range(args.warmup):
         reg.linearize(tc, tt, sc, poses[i % len(poses)])
@@ -392,8 +415,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle as O
 
-        threads = O.max_threads()
-        _, tc, tt, sc, reg, build_s = cpu_setup(inp, threads)
+        threads, (_, tc, tt, sc, reg, build_s) = best_cpu_registration(inp)
         reg.linearize(tc, tt, sc, poses[0])
         reps = 0
         t0 = time.perf_counter()
@@ -453,7 +475,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm",
-                "kernel": "sgb::linearize_kd_kernel<2,0>",
+                "kernel": "sgb::packet_search_kernel + sgb::factor_reduce_kernel<2,0> (the two launches of one linearize)",
                 "achieved": achieved,
                 "peak": peak,
                 "peak_source": peak_src,

@@ -66,9 +66,12 @@ int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points_xyz1, con
  * (ann/kdtree.hpp:237).  Any builder's node order is accepted (serial / OMP / TBB). Leaf scan order is
  * preserved, so exact-tie behaviour follows the reference's (ann/knn_result.hpp:80-83). */
 int sgb_target_set_kdtree(sgb_ctx* ctx, const void* nodes24, size_t n_nodes, uint32_t root, const uint64_t* indices);
-/* Or build this library's own kd-tree over the current target points (replaces
- * KdTreeBuilder::build_tree, ann/kdtree.hpp:74-131).  max_leaf_size <= 0 selects the default (32: one point
- * per lane of the warp-cooperative leaf scan; the reference's builder uses 20). */
+/* Or build this library's own kd-tree over the current target points ON THE DEVICE (replaces
+ * KdTreeBuilder::build_tree, ann/kdtree.hpp:74-131, and the OMP / TBB builders): Hilbert-order sort, then one radix sort
+ * per level along the widest axis of every node's box -- a balanced median-split kd-tree with at most 32 points per leaf
+ * (one per lane of the warp-cooperative leaf scan; the reference's builder uses 20), stored implicitly.  Asynchronous on
+ * the context's stream, no host round trip.  Exact nearest-neighbour results do not depend on the split choices (only
+ * exact ties can).  max_leaf_size is honoured only by the host-side profiling builder (SGB_TREE=host). */
 int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size);
 /* Gaussian voxel map target (VGICP): replaces IncrementalVoxelMap<GaussianVoxel>::nearest_neighbor_search
  * (ann/incremental_voxelmap.hpp:99-119) and its point/cov traits (:207-222).  Voxel i of the arrays is

@@ -72,6 +72,7 @@ int upload_tree(sgb_ctx* ctx, const FlatTree& tree, const float* host_pts_xyzw) 
   // the host vectors go out of scope when the caller returns: make sure the async copies are done
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->tree_depth = tree.depth;
+  ctx->tgt_has_kd = true;
   ctx->tgt_is_voxel = false;
   ctx->tgt_ready = true;
   ctx->have_lin = false;
@@ -250,6 +251,11 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   ctx->stream = ctx->own_stream;
   if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
   if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
+  if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
+    ctx->host_tree = (s[0] == 'h');
+    if (s[0] == 'l') ctx->tree_quality = 0;
+  }
+  if (ctx->search_mode != 2) ctx->host_tree = true;                        // the per-thread / fused kernels walk 8-byte kd nodes
   *out_ctx = ctx;
   return 0;
 }
@@ -357,6 +363,31 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
     return 0;
   }
   CU(cudaSetDevice(ctx->device));
+  if (ctx->search_mode == 2 && !ctx->host_tree) {
+    // device-side construction (linear BVH over the Hilbert order, sgb_kernels.cu): no host round trip, fully asynchronous
+    const size_t n = ctx->n_tgt;
+    int depth = 1;
+    if (int rc = build_lbvh(ctx, ctx->tgt_orig_pts.as<float4>(), n, ctx->tgt_centre.as<double>(), ctx->tgt_perm, ctx->tgt_pts, ctx->tgt_pnodes, &depth)) return rc;
+    if (depth > 40) return fail(ctx, 1, "sgb_target_build_kdtree: tree too deep");
+    if (ctx->tgt_has_normals) CU(ctx->tgt_normals.reserve(n * sizeof(float4)));
+    if (ctx->tgt_has_covs) {
+      CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
+      CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
+    }
+    if (ctx->tgt_has_normals || ctx->tgt_has_covs) {
+      CU(launch_gather(ctx->tgt_perm.as<uint32_t>(), n, nullptr, nullptr, ctx->tgt_has_normals ? ctx->tgt_orig_normals.as<float4>() : nullptr,
+                       ctx->tgt_normals.as<float4>(), ctx->tgt_has_covs ? ctx->tgt_orig_covA.as<float4>() : nullptr, ctx->tgt_covA.as<float4>(),
+                       ctx->tgt_has_covs ? ctx->tgt_orig_covB.as<float4>() : nullptr, ctx->tgt_covB.as<float4>(), ctx->sm_count, ctx->stream));
+      ctx->launches += 1;
+    }
+    ctx->tree_depth = depth;
+    ctx->tgt_has_kd = false;
+    ctx->tgt_is_voxel = false;
+    ctx->tgt_ready = true;
+    ctx->have_lin = false;
+    ctx->corr_seeds = false;
+    return 0;
+  }
   std::vector<float> pts(ctx->n_tgt * 4);
   CU(cudaMemcpyAsync(pts.data(), ctx->tgt_orig_pts.p, ctx->n_tgt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

@@ -11,33 +11,63 @@
 
 using namespace sgb;
 
-namespace {
+namespace sgb {
 
-constexpr int kFeatureLeaf = 10;  // leaf size of the throw-away tree used for the k-NN of the features
-
-/// Build this library's kd-tree over `n` centred float4 points that live on the device in original order;
-/// leaves `pre_nodes`, `pre_leaf_pts` (leaf order, w = original index) on the device and returns the depth.
-int build_feature_tree(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, int* depth_out) {
-  std::vector<float> pts(n * 4);
-  CU(cudaMemcpyAsync(pts.data(), d_orig_pts, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  FlatTree tree;
-  std::string err;
-  if (!build_flat_tree(pts.data(), n, kFeatureLeaf, tree, err)) return fail(ctx, 1, "feature kd-tree: " + err);
-  CU(ctx->pre_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
-  CU(ctx->pre_perm.reserve(n * sizeof(uint32_t)));
-  CU(ctx->pre_leaf_pts.reserve(n * sizeof(float4)));
-  CU(cudaMemcpyAsync(ctx->pre_nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->pre_perm.p, tree.perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CU(launch_gather(ctx->pre_perm.as<uint32_t>(), n, d_orig_pts, ctx->pre_leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                   ctx->sm_count, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));  // host vectors die at return
-  ctx->launches += 1;
-  *depth_out = tree.depth;
+/// Device-side construction of the search structure over `n` centred FP32 points (original order, w = index):
+/// Hilbert keys -> radix sort -> leaf-ordered points -> leaf boxes -> one kernel per level of the implicit binary tree.
+/// No host round trip, no synchronisation.  Outputs: perm (leaf order -> original index), leaf_pts, pnodes, depth.
+int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d_centre4, DevBuf& perm, DevBuf& leaf_pts, DevBuf& pnodes, int* depth) {
+  if (n >= (1ull << 30)) return fail(ctx, 1, "too many points for the device tree");
+  // P leaf slots (power of two), leaf j = positions [floor(j n / P), floor((j+1) n / P)): at most 32 points each
+  uint32_t P = 2;
+  int d = 1;
+  while (static_cast<uint64_t>(P) * kLbvhLeafPoints < n) {
+    P <<= 1;
+    d++;
+  }
+  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
+  CU(perm.reserve(n * sizeof(uint32_t)));
+  CU(leaf_pts.reserve(n * sizeof(float4)));
+  CU(pnodes.reserve(static_cast<size_t>(P - 1) * 64));
+  CU(launch_curve_keys(d_orig_pts, n, d_centre4, ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  size_t temp_bytes = 0;
+  CU(sort_pairs_u64_u32(nullptr, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), perm.as<uint32_t>(), n,
+                        ctx->stream));
+  CU(ctx->sort_temp.reserve(temp_bytes));
+  CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        perm.as<uint32_t>(), n, ctx->stream));
+  CU(launch_gather(perm.as<uint32_t>(), n, d_orig_pts, leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream));
+  ctx->launches += 5;
+  if (ctx->tree_quality >= 1) {
+    // median-split refinement: level by level, sort every node's points along the widest axis of its box; the balanced
+    // position boundaries of the next level are then exactly the median splits of a kd-tree (same quality as the host
+    // builder, ~d radix sorts instead of a D2H + recursive host build + H2D)
+    CU(ctx->pre_boxes.reserve(static_cast<size_t>(P) * 6 * sizeof(uint32_t)));
+    for (int level = 0; level < d; level++) {
+      const uint32_t count = 1u << level;
+      CU(launch_kd_level_keys(leaf_pts.as<float4>(), static_cast<uint32_t>(n), count, ctx->pre_boxes.as<uint32_t>(), ctx->keys_in.as<uint64_t>(), ctx->stream));
+      CU(cudaMemcpyAsync(ctx->vals_in.p, perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+      size_t tb = 0;
+      CU(sort_pairs_u64_u32_bits(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), perm.as<uint32_t>(), n,
+                                 32 + level, ctx->stream));
+      CU(ctx->sort_temp.reserve(tb));
+      CU(sort_pairs_u64_u32_bits(ctx->sort_temp.p, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                                 perm.as<uint32_t>(), n, 32 + level, ctx->stream));
+      CU(launch_gather(perm.as<uint32_t>(), n, d_orig_pts, leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sm_count,
+                       ctx->stream));
+      ctx->launches += 8;
+    }
+  }
+  int launches = 0;
+  CU(launch_lbvh_build(leaf_pts.as<float4>(), static_cast<uint32_t>(n), P, pnodes.as<float4>(), &launches, ctx->stream));
+  ctx->launches += launches;
+  *depth = d + 1;
   return 0;
 }
 
-}  // namespace
+}  // namespace sgb
 
 extern "C" {
 
@@ -58,11 +88,11 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
                     nullptr, ctx->sm_count, ctx->stream));
   ctx->launches += 4;
   int depth = 0;
-  if (int rc = build_feature_tree(ctx, ctx->pre_pts.as<float4>(), n, &depth)) return rc;
+  if (int rc = build_lbvh(ctx, ctx->pre_pts.as<float4>(), n, ctx->pre_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
   if (out_normals) CU(ctx->pre_out_normals.reserve(n * 4 * sizeof(double)));
   if (out_covs) CU(ctx->pre_out_covs.reserve(n * 16 * sizeof(double)));
   const int mode = (out_normals ? 1 : 0) | (out_covs ? 2 : 0);
-  CU(launch_features(ctx->pre_nodes.as<KdNode>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->pre_centre.as<double>(), mode,
+  CU(launch_features(ctx->pre_nodes.as<float4>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->pre_centre.as<double>(), mode,
                      nullptr, nullptr, nullptr, out_normals ? ctx->pre_out_normals.as<double>() : nullptr, out_covs ? ctx->pre_out_covs.as<double>() : nullptr,
                      depth, 0, ctx->stream));
   ctx->launches += 1;
@@ -86,7 +116,7 @@ int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
   CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
   // the target's own tree and leaf-ordered points are already resident: write the features straight into the leaf-ordered streams
-  CU(launch_features(ctx->tgt_nodes.as<KdNode>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->tgt_centre.as<double>(), 3,
+  CU(launch_features(ctx->tgt_pnodes.as<float4>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->tgt_centre.as<double>(), 3,
                      ctx->tgt_normals.as<float4>(), ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->tree_depth, 1, ctx->stream));
   ctx->launches += 1;
   return 0;
@@ -103,12 +133,12 @@ int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   CU(cudaSetDevice(ctx->device));
   // tmp_pts still holds the source in ORIGINAL order (centred FP32, w = index) from sgb_source_set_points
   int depth = 0;
-  if (int rc = build_feature_tree(ctx, ctx->tmp_pts.as<float4>(), n, &depth)) return rc;
+  if (int rc = build_lbvh(ctx, ctx->tmp_pts.as<float4>(), n, ctx->src_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
   CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
   CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
   CU(ctx->src_covA.reserve(n * sizeof(float4)));
   CU(ctx->src_covB.reserve(n * sizeof(float4)));
-  CU(launch_features(ctx->pre_nodes.as<KdNode>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->src_centre.as<double>(), 2, nullptr,
+  CU(launch_features(ctx->pre_nodes.as<float4>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->src_centre.as<double>(), 2, nullptr,
                      ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), nullptr, nullptr, depth, 0, ctx->stream));
   // original order -> the search order of the source (chunk-transposed Morton)
   CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_covA.as<float4>(), ctx->src_covA.as<float4>(), ctx->tmp_covB.as<float4>(), ctx->src_covB.as<float4>(),

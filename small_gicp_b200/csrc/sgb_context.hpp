@@ -52,6 +52,10 @@ struct sgb_ctx {
   sgb::DevBuf tgt_pts, tgt_normals, tgt_covA, tgt_covB;                      // leaf order (or voxel order)
   sgb::DevBuf tgt_nodes, tgt_perm, tgt_pnodes;  // kd nodes (8 B), leaf permutation, packet records (64 B / inner node)
   int tree_depth = 0;
+  bool tgt_has_kd = false;  // 8-byte kd nodes present (adopted / host-built trees); device-built trees only have packet records
+  bool host_tree = false;   // profiling switch: sgb_target_build_kdtree builds a median-split kd-tree on the host
+  int tree_quality = 1;     // device construction: 1 = Hilbert order + per-level median-split refinement (kd quality), 0 = Hilbert order only (linear BVH)
+  sgb::DevBuf pre_boxes;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;
   uint32_t vox_mask = 0;
@@ -89,6 +93,9 @@ inline int fail(sgb_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   return code;
 }
+
+/// device-side tree construction (sgb_capi_preprocess.cu)
+int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d_centre4, DevBuf& perm, DevBuf& leaf_pts, DevBuf& pnodes, int* depth);
 
 }  // namespace sgb
 

@@ -361,7 +361,42 @@ __device__ __forceinline__ uint64_t spread21(uint64_t x) {  // 21 bits -> every 
   return x;
 }
 
-// raw (double AoS) -> centred float4 in ORIGINAL order (w = index), optional features, optional Morton key
+
+/// 63-bit space-filling-curve key of a centred point (h = half extent of the cloud's box, inv_ext = (2^21 - 1) / extent).
+__device__ __forceinline__ uint64_t curve_key(double x, double y, double z, double h, double inv_ext) {
+  const uint64_t kx = static_cast<uint64_t>(fmin(fmax((x + h) * inv_ext, 0.0), 2097151.0));
+  const uint64_t ky = static_cast<uint64_t>(fmin(fmax((y + h) * inv_ext, 0.0), 2097151.0));
+  const uint64_t kz = static_cast<uint64_t>(fmin(fmax((z + h) * inv_ext, 0.0), 2097151.0));
+  if (!d_use_hilbert) return spread21(kx) | (spread21(ky) << 1) | (spread21(kz) << 2);  // Morton
+  // Hilbert index (Skilling's transpose algorithm, 21 bits x 3): unlike the Z-curve it has no jumps, so 32 consecutive
+  // points form a tighter patch
+  uint32_t X[3] = {static_cast<uint32_t>(kx), static_cast<uint32_t>(ky), static_cast<uint32_t>(kz)};
+  const uint32_t M = 1u << 20;
+  for (uint32_t Q = M; Q > 1; Q >>= 1) {
+    const uint32_t Pm = Q - 1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (X[a] & Q) {
+        X[0] ^= Pm;
+      } else {
+        const uint32_t t = (X[0] ^ X[a]) & Pm;
+        X[0] ^= t;
+        X[a] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  uint32_t t = 0;
+  for (uint32_t Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t;
+  X[1] ^= t;
+  X[2] ^= t;
+  return (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
+}
+
+// raw (double AoS) -> centred float4 in ORIGINAL order (w = index), optional features, optional curve key
 __global__ void convert_kernel(const double4* __restrict__ pts, const double4* __restrict__ normals, const double* __restrict__ covs, size_t n,
                                const double* __restrict__ centre, float4* out_pts, float4* out_normals, float4* out_covA, float4* out_covB,
                                uint64_t* keys, uint32_t* vals) {
@@ -381,43 +416,174 @@ __global__ void convert_kernel(const double4* __restrict__ pts, const double4* _
       out_covB[i] = pack_covB(c);
     }
     if (keys) {
-      const double h = 0.5 * centre[3];
-      const uint64_t kx = static_cast<uint64_t>(fmin(fmax((x + h) * inv_ext, 0.0), 2097151.0));
-      const uint64_t ky = static_cast<uint64_t>(fmin(fmax((y + h) * inv_ext, 0.0), 2097151.0));
-      const uint64_t kz = static_cast<uint64_t>(fmin(fmax((z + h) * inv_ext, 0.0), 2097151.0));
-      if (d_use_hilbert) {
-        // Hilbert index (Skilling's transpose algorithm, 21 bits x 3): unlike the Z-curve it has no jumps, so 32 consecutive
-        // points form a tighter patch
-        uint32_t X[3] = {static_cast<uint32_t>(kx), static_cast<uint32_t>(ky), static_cast<uint32_t>(kz)};
-        const uint32_t M = 1u << 20;
-        for (uint32_t Q = M; Q > 1; Q >>= 1) {
-          const uint32_t Pm = Q - 1;
-#pragma unroll
-          for (int a = 0; a < 3; a++) {
-            if (X[a] & Q) {
-              X[0] ^= Pm;
-            } else {
-              const uint32_t t = (X[0] ^ X[a]) & Pm;
-              X[0] ^= t;
-              X[a] ^= t;
-            }
-          }
-        }
-        X[1] ^= X[0];
-        X[2] ^= X[1];
-        uint32_t t = 0;
-        for (uint32_t Q = M; Q > 1; Q >>= 1)
-          if (X[2] & Q) t ^= Q - 1;
-        X[0] ^= t;
-        X[1] ^= t;
-        X[2] ^= t;
-        keys[i] = (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
-      } else {
-        keys[i] = spread21(kx) | (spread21(ky) << 1) | (spread21(kz) << 2);
-      }
+      keys[i] = curve_key(x, y, z, 0.5 * centre[3], inv_ext);
       vals[i] = static_cast<uint32_t>(i);
     }
   }
+}
+
+// curve keys of points that are already on the device in centred FP32 form (target: device-side tree construction)
+__global__ void curve_keys_kernel(const float4* __restrict__ pts, size_t n, const double* __restrict__ centre, uint64_t* keys, uint32_t* vals) {
+  const double inv_ext = 2097151.0 / centre[3], h = 0.5 * centre[3];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 p = pts[i];
+    keys[i] = curve_key(p.x, p.y, p.z, h, inv_ext);
+    vals[i] = static_cast<uint32_t>(i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side construction of the search structure (replaces KdTreeBuilder::build_tree, ann/kdtree.hpp:74-131, and its
+// OMP / TBB variants).  Exact nearest-neighbour results do not depend on how the hierarchy is formed, so instead of
+// recursive median splits the tree is a linear BVH: points sorted along the Hilbert curve, leaves = runs of kLbvhLeaf
+// consecutive points, hierarchy = the implicit perfect binary tree over P = 2^ceil(log2(#leaves)) leaf slots (node i has
+// children 2i+1, 2i+2; missing leaves are empty boxes that no query ever enters).  Every step is a data-parallel kernel;
+// the output is the same 64-byte packet record array the search kernel consumes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lbvh_store_child(float4* pnodes, uint32_t child_heap, const float lo[3], const float hi[3], uint32_t a, uint32_t b) {
+  const uint32_t parent = (child_heap - 1u) >> 1, side = (child_heap & 1u) ? 0u : 1u;  // odd heap index = left child
+  pnodes[parent * 4 + side * 2 + 0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(a));
+  pnodes[parent * 4 + side * 2 + 1] = make_float4(hi[0], hi[1], hi[2], __uint_as_float(b));
+}
+
+/// first point of node j at a level with `count` nodes (balanced implicit tree over n points)
+__device__ __forceinline__ uint32_t tree_bound(uint32_t j, uint32_t count, uint32_t n) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(j) * n) / count);
+}
+/// node (at a level with `count` nodes) that owns position i
+__device__ __forceinline__ uint32_t tree_node_of(uint32_t i, uint32_t count, uint32_t n) {
+  return static_cast<uint32_t>(((static_cast<uint64_t>(i) + 1u) * count + n - 1u) / n) - 1u;
+}
+
+// ---- median-split refinement (device-side kd construction): one pass per level ------------------------------------
+// boxes: count x 6 floats stored as order-preserving uints (lo xyz, hi xyz)
+__device__ __forceinline__ uint32_t float_flip(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float float_unflip(uint32_t u) { return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
+
+__global__ void kd_boxes_init_kernel(uint32_t* boxes, uint32_t count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count * 6u) boxes[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
+}
+
+__global__ void kd_boxes_kernel(const float4* __restrict__ pts, uint32_t n, uint32_t count, uint32_t* boxes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  const uint32_t idx = valid ? i : n - 1u;
+  const float4 p = pts[idx];
+  const uint32_t node = tree_node_of(idx, count, n);
+  uint32_t v[6] = {float_flip(p.x), float_flip(p.y), float_flip(p.z), float_flip(p.x), float_flip(p.y), float_flip(p.z)};
+  // warp-level pre-reduction when the whole warp sits in one node (all but the deepest levels)
+  const uint32_t node0 = __shfl_sync(0xffffffffu, node, 0);
+  if (__all_sync(0xffffffffu, node == node0)) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      v[a] = __reduce_min_sync(0xffffffffu, v[a]);
+      v[3 + a] = __reduce_max_sync(0xffffffffu, v[3 + a]);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        atomicMin(&boxes[node * 6 + a], v[a]);
+        atomicMax(&boxes[node * 6 + 3 + a], v[3 + a]);
+      }
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      atomicMin(&boxes[node * 6 + a], v[a]);
+      atomicMax(&boxes[node * 6 + 3 + a], v[3 + a]);
+    }
+  }
+}
+
+// key = (node << 32) | coordinate along the node's widest axis: sorting by it orders every node's points along its split
+// axis, and the balanced position boundaries of the next level then ARE the median splits
+__global__ void kd_keys_kernel(const float4* __restrict__ pts, uint32_t n, uint32_t count, const uint32_t* __restrict__ boxes, uint64_t* keys) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t node = tree_node_of(i, count, n);
+  const float ex = float_unflip(boxes[node * 6 + 3]) - float_unflip(boxes[node * 6 + 0]);
+  const float ey = float_unflip(boxes[node * 6 + 4]) - float_unflip(boxes[node * 6 + 1]);
+  const float ez = float_unflip(boxes[node * 6 + 5]) - float_unflip(boxes[node * 6 + 2]);
+  const float4 p = pts[i];
+  const float c = ex >= ey ? (ex >= ez ? p.x : p.z) : (ey >= ez ? p.y : p.z);
+  keys[i] = (static_cast<uint64_t>(node) << 32) | float_flip(c);
+}
+
+// one warp per leaf slot: bounding box of its (at most 32) consecutive points -> the parent's child record
+__global__ void lbvh_leaf_kernel(const float4* __restrict__ leaf_pts, uint32_t n, uint32_t P, float4* pnodes) {
+  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (slot >= P) return;
+  const uint32_t first = tree_bound(slot, P, n), last = tree_bound(slot + 1u, P, n), idx = first + lane;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (idx < last) {
+    const float4 p = leaf_pts[idx];
+    lo[0] = hi[0] = p.x;
+    lo[1] = hi[1] = p.y;
+    lo[2] = hi[2] = p.z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  }
+  if (lane == 0) {
+    const uint32_t cnt = last - first;
+    lbvh_store_child(pnodes, (P - 1u) + slot, lo, hi, cnt ? first : 0u, cnt);  // cnt == 0: inverted box, never entered
+  }
+}
+
+// one thread per inner node of a level (children records complete): union box -> the parent's child record
+__global__ void lbvh_level_kernel(uint32_t level_first, uint32_t level_count, float4* pnodes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= level_count) return;
+  const uint32_t node = level_first + t;
+  const float4 l0 = pnodes[node * 4 + 0], l1 = pnodes[node * 4 + 1], r0 = pnodes[node * 4 + 2], r1 = pnodes[node * 4 + 3];
+  const float lo[3] = {fminf(l0.x, r0.x), fminf(l0.y, r0.y), fminf(l0.z, r0.z)};
+  const float hi[3] = {fmaxf(l1.x, r1.x), fmaxf(l1.y, r1.y), fmaxf(l1.z, r1.z)};
+  lbvh_store_child(pnodes, node, lo, hi, node, 0u);  // inner child: a = node index, b = 0
+}
+
+cudaError_t launch_curve_keys(const float4* pts, size_t n, const double* centre4, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  size_t g = (n + 255) / 256;
+  if (g > static_cast<size_t>(sm_count) * 8) g = static_cast<size_t>(sm_count) * 8;
+  curve_keys_kernel<<<static_cast<int>(g), 256, 0, st>>>(pts, n, centre4, keys, vals);
+  return cudaGetLastError();
+}
+
+/// pnodes: (P - 1) * 4 float4 records, P = number of leaf slots (power of two >= 2).  Returns the number of launches in *launches.
+cudaError_t launch_lbvh_build(const float4* leaf_pts, uint32_t n, uint32_t P, float4* pnodes, int* launches, cudaStream_t st) {
+  const uint32_t warps_per_block = 8;
+  lbvh_leaf_kernel<<<(P + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(leaf_pts, n, P, pnodes);
+  int count = 1;
+  for (uint32_t level_count = P >> 1; level_count >= 2; level_count >>= 1) {  // deepest inner level first; the root (level_count 1) has no parent
+    const uint32_t level_first = level_count - 1u;
+    lbvh_level_kernel<<<(level_count + 255) / 256, 256, 0, st>>>(level_first, level_count, pnodes);
+    count++;
+  }
+  if (launches) *launches = count;
+  return cudaGetLastError();
+}
+
+/// One level of the median-split refinement: boxes of the `count` nodes of this level over the points in their current
+/// order, then the sort keys.  The caller sorts (keys, perm) and re-gathers the points.
+cudaError_t launch_kd_level_keys(const float4* cur_pts, uint32_t n, uint32_t count, uint32_t* boxes, uint64_t* keys, cudaStream_t st) {
+  kd_boxes_init_kernel<<<(count * 6u + 255u) / 256u, 256, 0, st>>>(boxes, count);
+  kd_boxes_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(cur_pts, n, count, boxes);
+  kd_keys_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(cur_pts, n, count, boxes, keys);
+  return cudaGetLastError();
+}
+
+cudaError_t sort_pairs_u64_u32_bits(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                                    size_t n, int end_bit, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0, end_bit, st);
 }
 
 // out[j] = in[perm[j]] for up to four float4 streams (leaf ordering of the target / Morton ordering of the source)

@@ -31,8 +31,15 @@ cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t*
 // sgb_kernels_packet.cu
 int packet_occupancy(int max_depth);
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, cudaStream_t st);
+// device-side tree construction (sgb_kernels.cu)
+constexpr uint32_t kLbvhLeafPoints = 32;
+cudaError_t launch_curve_keys(const float4* pts, size_t n, const double* centre4, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);
+cudaError_t launch_lbvh_build(const float4* leaf_pts, uint32_t n, uint32_t P, float4* pnodes, int* launches, cudaStream_t st);
+cudaError_t launch_kd_level_keys(const float4* cur_pts, uint32_t n, uint32_t count, uint32_t* boxes, uint64_t* keys, cudaStream_t st);
+cudaError_t sort_pairs_u64_u32_bits(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                                    size_t n, int end_bit, cudaStream_t st);
 // sgb_preprocess.cu
-cudaError_t launch_features(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
+cudaError_t launch_features(const float4* pnodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
                             float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st);
 cudaError_t launch_voxel_keys(const double* d_pts4, size_t n, double inv_leaf, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);
 cudaError_t launch_voxel_heads(const uint64_t* keys, size_t n, uint32_t* heads, int sm_count, cudaStream_t st);

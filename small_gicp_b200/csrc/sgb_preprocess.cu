@@ -53,46 +53,71 @@ struct KnnList {
   }
 };
 
+__device__ __forceinline__ float pre_box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
+  const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+  const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+  const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+/// Exact k-NN of one query per thread in the packet (BVH2) records of the cloud's tree (sgb_kernels_packet.cu has the
+/// record layout): near child first, the far child is kept pending only while its box is closer than the k-th distance.
+/// stack entry s of thread t: desc[s * kLinBlock + t] (child descriptor) and dist[s * kLinBlock + t] (its box distance).
 template <int KMAX>
-__device__ __forceinline__ void kd_knn(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, float qx, float qy, float qz, KnnList<KMAX>& L,
-                                       uint2* stack) {
-  uint32_t node = 0;
+__device__ __forceinline__ void bvh_knn(const float4* __restrict__ pnodes, const float4* __restrict__ pts, float qx, float qy, float qz, KnnList<KMAX>& L,
+                                        uint2* desc, float* dist) {
   int sp = 0;
-  uint2* my_stack = stack + threadIdx.x;
+  uint2* my_desc = desc + threadIdx.x;
+  float* my_dist = dist + threadIdx.x;
+  uint32_t cur = 0;
+  bool expand = true;
+  uint2 leaf = make_uint2(0u, 0u);
   for (;;) {
-    KdNode nd = __ldg(&nodes[node]);
-    uint32_t kind = nd.y & 3u;
-    while (kind != 3u) {
-      const float qv = kind == 0u ? qx : (kind == 1u ? qy : qz);
-      const float diff = qv - __uint_as_float(nd.x);
-      const uint32_t right = nd.y >> 2, left = node + 1u;
-      const bool go_left = diff < 0.0f;
-      const float cut = diff * diff;
-      if (cut < L.worst) {
-        my_stack[sp * kLinBlock] = make_uint2(go_left ? right : left, __float_as_uint(cut));
+    if (expand) {
+      const float4 n0 = __ldg(&pnodes[cur * 4 + 0]), n1 = __ldg(&pnodes[cur * 4 + 1]);
+      const float4 n2 = __ldg(&pnodes[cur * 4 + 2]), n3 = __ldg(&pnodes[cur * 4 + 3]);
+      const float dl = pre_box_dist2(qx, qy, qz, n0, n1), dr = pre_box_dist2(qx, qy, qz, n2, n3);
+      const bool left_first = dl <= dr;
+      const float dn = left_first ? dl : dr, df = left_first ? dr : dl;
+      const uint2 cn = left_first ? make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w)) : make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w));
+      const uint2 cf = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
+      if (df < L.worst) {
+        my_desc[sp * kLinBlock] = cf;
+        my_dist[sp * kLinBlock] = df;
         sp++;
       }
-      node = go_left ? left : right;
-      nd = __ldg(&nodes[node]);
-      kind = nd.y & 3u;
-    }
-    const uint32_t first = nd.x, cnt = nd.y >> 2;
-    for (uint32_t j = 0; j < cnt; j++) {
-      const float4 t = __ldg(&pts[first + j]);
-      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-      L.offer(dx * dx + dy * dy + dz * dz, first + j);
-    }
-    bool found = false;
-    while (sp > 0) {
-      sp--;
-      const uint2 e = my_stack[sp * kLinBlock];
-      if (__uint_as_float(e.y) < L.worst) {  // worst_distance() > cut_sq_dist, ann/kdtree.hpp:228
-        node = e.x;
-        found = true;
-        break;
+      if (!(dn < L.worst)) {
+        expand = false;
+        continue;
+      }
+      if (cn.y == 0u) {
+        cur = cn.x;
+        continue;
+      }
+      leaf = cn;
+    } else {
+      bool got = false;
+      while (sp > 0) {
+        sp--;
+        if (my_dist[sp * kLinBlock] < L.worst) {  // worst_distance() > lower bound of the subtree (ann/kdtree.hpp:228 analogue)
+          leaf = my_desc[sp * kLinBlock];
+          got = true;
+          break;
+        }
+      }
+      if (!got) break;
+      if (leaf.y == 0u) {
+        cur = leaf.x;
+        expand = true;
+        continue;
       }
     }
-    if (!found) break;
+    for (uint32_t j = 0; j < leaf.y; j++) {
+      const float4 t = __ldg(&pts[leaf.x + j]);
+      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+      L.offer(dx * dx + dy * dy + dz * dz, leaf.x + j);
+    }
+    expand = false;
   }
 }
 
@@ -161,16 +186,16 @@ __device__ __forceinline__ void smallest_eigenvector(double a00, double a01, dou
 /// mode bit 0: normals, bit 1: covariances.  Outputs are written in the cloud's ORIGINAL order
 /// (index carried in pts[].w): device layout (float4 streams) and / or the reference's double layout.
 template <int KMAX>
-__global__ void __launch_bounds__(kLinBlock) features_kernel(const KdNode* __restrict__ nodes, const float4* __restrict__ pts, uint32_t n, int k,
+__global__ void __launch_bounds__(kLinBlock) features_kernel(const float4* __restrict__ pnodes, const float4* __restrict__ pts, uint32_t n, int k,
                                                              const double* __restrict__ centre, int mode, float4* out_normals, float4* out_covA,
-                                                             float4* out_covB, double* out_normals_d, double* out_covs_d, int leaf_order_out) {
-  extern __shared__ uint2 s_stack[];
+                                                             float4* out_covB, double* out_normals_d, double* out_covs_d, int leaf_order_out, int depth) {
+  extern __shared__ uint2 s_stack[];  // [depth][kLinBlock] descriptors, then [depth][kLinBlock] distances
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = __ldg(&pts[i]);
   KnnList<KMAX> L;
   L.init(k);
-  kd_knn<KMAX>(nodes, pts, q.x, q.y, q.z, L, s_stack);
+  bvh_knn<KMAX>(pnodes, pts, q.x, q.y, q.z, L, s_stack, reinterpret_cast<float*>(s_stack + static_cast<size_t>(depth) * kLinBlock));
   int found = 0;
   // sums relative to the query point (covariance is translation invariant; keeps the FP64 sums well conditioned)
   double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};
@@ -227,19 +252,20 @@ __global__ void __launch_bounds__(kLinBlock) features_kernel(const KdNode* __res
 }
 
 template <int KMAX>
-static cudaError_t launch_features_t(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* on, float4* oa, float4* ob,
+static cudaError_t launch_features_t(const float4* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* on, float4* oa, float4* ob,
                                      double* ond, double* ocd, int depth, int leaf_order_out, cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(depth > 0 ? depth : 1) * kLinBlock * sizeof(uint2);
+  if (depth < 1) depth = 1;
+  const size_t smem = static_cast<size_t>(depth) * kLinBlock * (sizeof(uint2) + sizeof(float));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(features_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
   const int grid = static_cast<int>((n + kLinBlock - 1) / kLinBlock);
-  features_kernel<KMAX><<<grid, kLinBlock, smem, st>>>(nodes, pts, n, k, centre, mode, on, oa, ob, ond, ocd, leaf_order_out);
+  features_kernel<KMAX><<<grid, kLinBlock, smem, st>>>(nodes, pts, n, k, centre, mode, on, oa, ob, ond, ocd, leaf_order_out, depth);
   return cudaGetLastError();
 }
 
-cudaError_t launch_features(const KdNode* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
+cudaError_t launch_features(const float4* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
                             float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   if (k <= 10) return launch_features_t<10>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);

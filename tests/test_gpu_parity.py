@@ -289,6 +289,34 @@ def test_synthetic_200k_gicp(synthetic_pair):
     ctx2.close()
 
 
+def test_search_structures_agree(synthetic_pair, monkeypatch):
+    """Exact NN is independent of the search structure: device-built linear BVH (default), host-built median-split
+    kd-tree, adopted reference kd-tree; packet, per-thread and fused kernels -- same correspondences, same sums."""
+    tc, tt, sc, Tgt, nt = synthetic_pair
+    sg = _sg()
+    results = {}
+    for name, env, own in (
+        ("device-lbvh/packet", {}, True),
+        ("host-kd/packet", {"SGB_TREE": "host"}, True),
+        ("reference-kd/packet", {}, False),
+        ("reference-kd/per-thread", {"SGB_SEARCH": "1"}, False),
+        ("host-kd/fused", {"SGB_SEARCH": "0"}, True),
+    ):
+        for k in ("SGB_TREE", "SGB_SEARCH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = load_ctx(tc, tt, sc, own_tree=own)
+        ctx.linearize(np.eye(4))  # also exercises the seeded second search
+        H, b, e = ctx.linearize(Tgt)
+        results[name] = (H, b, e, ctx.correspondences())
+        ctx.close()
+    H0, b0, e0, c0 = results["reference-kd/packet"]
+    for name, (H, b, e, c) in results.items():
+        assert (c != c0).sum() <= 3, name
+        assert np.linalg.norm(H - H0) <= 1e-6 * np.linalg.norm(H0) and abs(e - e0) <= 1e-6 * e0, name
+
+
 def test_full_size_properties():
     """BASELINE config 2 full size (1M x 1M): size-independent properties instead of an oracle run.
       * own-tree NN == brute-force NN on a random sample of queries (exactness)
