@@ -177,17 +177,33 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle's OpenMP reduction on this box's host cores
 # ------------------------------------------------------------------------------------------------
+def cpu_kind():
+    """("reference", lib) when oracle/_ref exists -- the reference's OWN headers compiled in place against the Eigen API shim
+    (oracle/ref_build; built in the dev container, shipped as a .so) -- else ("port", None): the oracle's restatement."""
+    import oracle as O
+
+    ref = O.reference_lib()
+    return ("reference", ref) if ref is not None else ("port", None)
+
+
+CPU_NOTE = {
+    "reference": "small_gicp's own headers (ParallelReductionOMP<GICPFactor>, schedule(guided,8)) compiled against an Eigen API shim: the reference's code, but without Eigen's SIMD kernels; -O3, no -march=native",
+    "port": "oracle restatement of reduction_omp.hpp (schedule(guided,8)); not the reference binary, no Eigen SIMD; -O3, no -march=native",
+}
+
+
 def cpu_setup(inp, threads):
     import oracle as O
 
-    tc = O.Cloud(inp["target"])
-    sc = O.Cloud(inp["source"])
+    kind, lib = cpu_kind()
+    tc = O.Cloud(inp["target"], _lib=lib)
+    sc = O.Cloud(inp["source"], _lib=lib)
     t0 = time.perf_counter()
     tt = O.KdTree(tc)
     build_s = time.perf_counter() - t0
     tc.set_features(None, inp["target_covs"])
     sc.set_features(None, inp["source_covs"])
-    reg = O.Registration(factor=O.FACTOR_GICP, rejector=O.REJECT_DISTANCE, max_dist_sq=1.0, num_threads=threads)
+    reg = O.Registration(factor=O.FACTOR_GICP, rejector=O.REJECT_DISTANCE, max_dist_sq=1.0, num_threads=threads, _lib=lib)
     return O, tc, tt, sc, reg, build_s
 
 
@@ -223,7 +239,7 @@ def run_reference(args):
     threads = host_threads()
 
     def oracle_covs(p4):  # the reference arm prepares its inputs with the CPU oracle only (none of our kernels on this arm)
-        c = O.Cloud(p4)
+        c = O.Cloud(p4, _lib=cpu_kind()[1])
         t = O.KdTree(c)
         t.estimate(20, O.FEAT_COV, threads)
         return c.covs
@@ -258,8 +274,8 @@ def run_reference(args):
             "value": value,
             "unit": UNIT,
             "cores": threads,
-            "kind": "port",
-            "sample": f"{args.steps} x Reduction::linearize over all {args.points} source points (oracle restatement of reduction_omp.hpp, schedule(guided,8), -O3 without -march=native; not the reference binary, no Eigen SIMD)",
+            "kind": cpu_kind()[0],
+            "sample": f"{args.steps} x Reduction::linearize over all {args.points} source points; " + CPU_NOTE[cpu_kind()[0]],
             "nproc": os.cpu_count(),
             "kdtree_build_s": build_s,
         },
@@ -429,8 +445,8 @@ def run_ours(args):
             "value": args.points / (cpu_ms * 1e-3) / 1e6,
             "unit": UNIT,
             "cores": threads,
-            "kind": "port",
-            "sample": f"{reps} x linearize over all {args.points} source points at the GN poses (oracle restatement of reduction_omp.hpp, guided,8; -O3, no -march=native; not the reference binary, no Eigen SIMD)",
+            "kind": cpu_kind()[0],
+            "sample": f"{reps} x linearize over all {args.points} source points at the GN poses; " + CPU_NOTE[cpu_kind()[0]],
             "nproc": os.cpu_count(),
             "ms_per_step": cpu_ms,
             "kdtree_build_s": build_s,

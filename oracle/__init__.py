@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_REF = None
+_SIGNATURES = {}
 
 FACTOR_ICP, FACTOR_PLANE, FACTOR_GICP = 0, 1, 2
 ROBUST_NONE, ROBUST_HUBER, ROBUST_CAUCHY = 0, 1, 2
@@ -75,6 +77,7 @@ def lib(native=False):
         "orc_ldlt_solve6": (None, [_dp, _dp, _dp]),
         "orc_eigen_sym3": (None, [_dp, _dp, _dp]),
     }
+    _SIGNATURES.update(sig)
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -82,6 +85,29 @@ def lib(native=False):
     if not native:
         _LIB = L
     return L
+
+
+def reference_lib():
+    """oracle/_ref/libsmallgicp_ref.so: the reference's OWN headers compiled against the Eigen API shim (oracle/ref_build), exposing the
+    same C API.  Built only where /root/reference exists; returns None when it is absent."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libsmallgicp_ref.so")
+        mk = os.path.join(_HERE, "ref_build", "Makefile")
+        if not os.path.exists(path) and os.path.isdir("/root/reference") and os.path.exists(mk):
+            subprocess.check_call(["make", "-s", "-C", os.path.dirname(mk)])
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        base = lib()
+        for name in dir(base):
+            pass
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _REF = L
+    return _REF
 
 
 def _d(a):
@@ -234,8 +260,8 @@ class Registration:
     num_threads = 0 -> SerialReduction ; > 0 -> ParallelReductionOMP(num_threads).
     """
 
-    def __init__(self, factor=FACTOR_GICP, robust=ROBUST_NONE, robust_c=1.0, rejector=REJECT_DISTANCE, max_dist_sq=1.0, num_threads=0, native=False):
-        self._L = lib(native)
+    def __init__(self, factor=FACTOR_GICP, robust=ROBUST_NONE, robust_c=1.0, rejector=REJECT_DISTANCE, max_dist_sq=1.0, num_threads=0, native=False, _lib=None):
+        self._L = _lib or lib(native)
         self._h = self._L.orc_reg_create(factor, robust, float(robust_c), rejector, float(max_dist_sq), num_threads)
         self.set_optimizer()
 

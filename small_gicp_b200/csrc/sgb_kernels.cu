@@ -475,7 +475,15 @@ __global__ void kd_boxes_kernel(const float4* __restrict__ pts, uint32_t n, uint
   const float4 p = pts[idx];
   const uint32_t node = tree_node_of(idx, count, n);
   uint32_t v[6] = {float_flip(p.x), float_flip(p.y), float_flip(p.z), float_flip(p.x), float_flip(p.y), float_flip(p.z)};
-  // warp-level pre-reduction when the whole warp sits in one node (all but the deepest levels)
+  // pre-reduction: whole CTA in one node (upper levels: otherwise thousands of atomics hit the same six words), else
+  // whole warp in one node, else per-thread atomics (deepest levels, little contention)
+  __shared__ uint32_t s_box[6];
+  __shared__ uint32_t s_first_node, s_last_node;
+  if (threadIdx.x == 0) s_first_node = node;
+  if (threadIdx.x == blockDim.x - 1) s_last_node = node;
+  if (threadIdx.x < 6) s_box[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+  __syncthreads();
+  const bool cta_uniform = s_first_node == s_last_node;  // positions are contiguous: equal ends => one node
   const uint32_t node0 = __shfl_sync(0xffffffffu, node, 0);
   if (__all_sync(0xffffffffu, node == node0)) {
 #pragma unroll
@@ -484,11 +492,17 @@ __global__ void kd_boxes_kernel(const float4* __restrict__ pts, uint32_t n, uint
       v[3 + a] = __reduce_max_sync(0xffffffffu, v[3 + a]);
     }
     if ((threadIdx.x & 31u) == 0) {
+      uint32_t* dst = cta_uniform ? s_box : &boxes[node * 6];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        atomicMin(&boxes[node * 6 + a], v[a]);
-        atomicMax(&boxes[node * 6 + 3 + a], v[3 + a]);
+        atomicMin(&dst[a], v[a]);
+        atomicMax(&dst[3 + a], v[3 + a]);
       }
+    }
+    if (cta_uniform) {
+      __syncthreads();
+      if (threadIdx.x < 3) atomicMin(&boxes[node * 6 + threadIdx.x], s_box[threadIdx.x]);
+      if (threadIdx.x >= 3 && threadIdx.x < 6) atomicMax(&boxes[node * 6 + threadIdx.x], s_box[threadIdx.x]);
     }
   } else if (valid) {
 #pragma unroll
