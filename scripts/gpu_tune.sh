@@ -1,10 +1,10 @@
 #!/bin/bash
-TAG=${1:-r01j}
+TAG=${1:-r01m}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== pytest -m gpu" | tee $OUT/pytest.log
 timeout 1200 python -m pytest tests -q -m gpu >> $OUT/pytest.log 2>&1; echo "rc=$?" >> $OUT/pytest.log
-tail -6 $OUT/pytest.log
+tail -12 $OUT/pytest.log
 show() {
 python - <<PY
 import json
@@ -15,22 +15,19 @@ except Exception as e:
     print("fail", e); print(open("$1".replace(".json",".err")).read()[-1500:])
 PY
 }
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_devkd.json 2> $OUT/bench_devkd.err
-show $OUT/bench_devkd.json "device kd (refined)"
-SGB_TREE=lbvh timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_lbvh.json 2> $OUT/bench_lbvh.err
-show $OUT/bench_lbvh.json "device LBVH"
-python - <<'PY'
-# build-time comparison of the three constructions on the 1M target
-import time, numpy as np, os
-import small_gicp_b200 as sg
-from small_gicp_b200.synthetic import make_pair
-tgt, src, T = make_pair(1_000_000)
-for name, env in (("device-kd", None), ("lbvh", "lbvh"), ("host-kd", "host")):
-    if env: os.environ["SGB_TREE"] = env
-    else: os.environ.pop("SGB_TREE", None)
-    ctx = sg.Context(0); ctx.set_target(tgt); ctx.build_target_kdtree(); ctx.synchronize()
-    ts = []
-    for _ in range(3):
-        t0 = time.perf_counter(); ctx.build_target_kdtree(); ctx.synchronize(); ts.append(time.perf_counter() - t0)
-    print(name, "build ms", [round(t * 1e3, 2) for t in ts]); ctx.close()
+for g in 1 0; do
+SGB_GRID=$g timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_grid$g.json 2> $OUT/bench_grid$g.err
+show $OUT/bench_grid$g.json "grid=$g"
+done
+echo "== ncu launch list of the timed region (grid on)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"packet_search|factor_reduce|grid_probe" -s 30 -c 60 --csv --log-file $OUT/launches_timed.csv \
+    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
+python - <<PY
+import csv,collections
+rows=list(csv.reader(open("$OUT/launches_timed.csv")))
+for i,r in enumerate(rows):
+    if 'Kernel Name' in r: hdr=r; start=i+1; break
+ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+seq=[(r[ki][:30], float(r[vi].replace(',',''))/1e3) for r in rows[start:] if len(r)>vi]
+for k,v in seq[:18]: print(f"{k:32s} {v:8.1f} us")
 PY

@@ -77,7 +77,8 @@ int upload_tree(sgb_ctx* ctx, const FlatTree& tree, const float* host_pts_xyzw) 
   ctx->tgt_ready = true;
   ctx->have_lin = false;
   ctx->corr_seeds = false;
-  return 0;
+  ctx->n_pnodes = pnodes.size();
+  return build_grid(ctx);
 }
 
 int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
@@ -158,7 +159,33 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
     if (ctx->search_mode == 2 && ctx->src_run == 1) {
       const int scap = ctx->sm_count * packet_occupancy(depth);
       if (sgrid > scap) sgrid = scap;
-      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, ctx->stream));
+      const uint8_t* settled = nullptr;
+      const uint32_t* pending_count = nullptr;
+      const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / 8);  // more pending than this: warp-cooperative search, else per-thread
+      if (ctx->grid_ready) {
+        // grid front end: settles every query whose nearest neighbour lies within half a cell (sgb_grid.cu)
+        CU(ctx->grid_state.reserve(ctx->n_src));
+        GridParams g;
+        for (int a = 0; a < 3; a++) g.origin[a] = ctx->grid_origin[a];
+        g.inv_cell = ctx->grid_inv_cell;
+        g.settle_d2 = ctx->grid_settle_d2;
+        CU(ctx->grid_pending.reserve((ctx->n_src + 1) * sizeof(uint32_t)));
+        uint32_t* pc = ctx->grid_pending.as<uint32_t>();
+        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_state.as<uint8_t>(), pc, pc + 1,
+                             ctx->stream));
+        CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, pc + 1, pending_split, ctx->sm_count * 4, ctx->stream));
+        ctx->launches += 2;
+        settled = ctx->grid_state.as<uint8_t>();
+        pending_count = pc;
+      }
+      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, ctx->stream));
+      static const bool debug_pending = std::getenv("SGB_DEBUG_PENDING") != nullptr;  // profiling aid: synchronises
+      if (debug_pending && pending_count) {
+        uint32_t h = 0;
+        CU(cudaMemcpyAsync(&h, pending_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::fprintf(stderr, "[sgb] grid front end: %u of %zu queries pending (cell %.4g)\n", h, ctx->n_src, ctx->grid_cell);
+      }
     } else {
       const int scap = ctx->sm_count * search_occupancy(depth);
       if (sgrid > scap) sgrid = scap;
@@ -251,6 +278,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   ctx->stream = ctx->own_stream;
   if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
   if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
+  if (const char* s = getenv("SGB_GRID")) ctx->use_grid = !(s[0] == '0');  // profiling switch: 0 = tree search only
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
     ctx->host_tree = (s[0] == 'h');
     if (s[0] == 'l') ctx->tree_quality = 0;
@@ -268,7 +296,7 @@ void sgb_destroy(sgb_ctx* ctx) {
                     &ctx->tgt_covB,     &ctx->tgt_nodes,        &ctx->tgt_perm, &ctx->tgt_pnodes,     &ctx->tgt_centre,    &ctx->tgt_bounds, &ctx->vox_table, &ctx->src_pts,
                     &ctx->src_covA,     &ctx->src_covB,         &ctx->src_perm,      &ctx->src_centre,    &ctx->src_bounds, &ctx->stage_pts, &ctx->stage_normals,
                     &ctx->stage_covs,   &ctx->tmp_pts,          &ctx->tmp_covA,      &ctx->tmp_covB,      &ctx->keys_in,  &ctx->keys_out,    &ctx->vals_in,
-                    &ctx->pre_pts, &ctx->pre_leaf_pts, &ctx->pre_nodes, &ctx->pre_perm, &ctx->pre_centre, &ctx->pre_bounds, &ctx->pre_out_normals, &ctx->pre_out_covs, &ctx->pre_heads, &ctx->pre_slots, &ctx->pre_vals_out,
+                    &ctx->pre_boxes, &ctx->grid_pending, &ctx->grid_pts, &ctx->grid_table, &ctx->grid_state, &ctx->grid_spacing, &ctx->pre_pts, &ctx->pre_leaf_pts, &ctx->pre_nodes, &ctx->pre_perm, &ctx->pre_centre, &ctx->pre_bounds, &ctx->pre_out_normals, &ctx->pre_out_covs, &ctx->pre_heads, &ctx->pre_slots, &ctx->pre_vals_out,
                     &ctx->sort_temp,    &ctx->corr,             &ctx->partials,      &ctx->ticket,        &ctx->out44,    &ctx->corr64};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -307,6 +335,7 @@ int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   ctx->tgt_has_normals = normals != nullptr;
   ctx->tgt_has_covs = covs != nullptr;
   ctx->tgt_ready = false;
+  ctx->grid_ready = false;
   ctx->tgt_is_voxel = false;
   ctx->have_lin = false;
   ctx->corr_seeds = false;
@@ -386,7 +415,8 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
     ctx->tgt_ready = true;
     ctx->have_lin = false;
     ctx->corr_seeds = false;
-    return 0;
+    ctx->n_pnodes = (static_cast<size_t>(1) << (depth - 1)) - 1;  // P - 1 records of the implicit tree (depth = log2(P) + 1)
+    return build_grid(ctx);
   }
   std::vector<float> pts(ctx->n_tgt * 4);
   CU(cudaMemcpyAsync(pts.data(), ctx->tgt_orig_pts.p, ctx->n_tgt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -408,6 +438,7 @@ int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, con
   ctx->tgt_has_normals = false;
   ctx->tgt_has_covs = covs != nullptr;
   ctx->tgt_is_voxel = true;
+  ctx->grid_ready = false;
   ctx->tgt_ready = true;
   ctx->have_lin = false;
   ctx->corr_seeds = false;

@@ -1,6 +1,8 @@
 // SPDX-License-Identifier: MIT
 // C-ABI entry points of the per-cloud preparation steps: normal / covariance estimation and
 // voxel-grid down-sampling on the device.  Kernels: sgb_preprocess.cu.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -64,6 +66,66 @@ int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d
   CU(launch_lbvh_build(leaf_pts.as<float4>(), static_cast<uint32_t>(n), P, pnodes.as<float4>(), &launches, ctx->stream));
   ctx->launches += launches;
   *depth = d + 1;
+  return 0;
+}
+
+/// Uniform grid over the leaf-ordered target points.  Cell edge = 3 x the median point spacing of the tree's leaves, so the
+/// settle radius (half a cell) is ~3 mean nearest-neighbour distances of a surface sampled like the target.
+int build_grid(sgb_ctx* ctx) {
+  ctx->grid_ready = false;
+  const size_t n = ctx->n_tgt;
+  if (!ctx->use_grid || ctx->search_mode != 2 || ctx->tgt_is_voxel || n < 1024 || ctx->n_pnodes == 0) return 0;
+  // spacing estimate from the leaf boxes + the target box (one small D2H, construction is a per-target one-off)
+  const size_t m = ctx->n_pnodes * 2;
+  CU(ctx->grid_spacing.reserve(m * sizeof(float)));
+  CU(launch_grid_spacing(ctx->tgt_pnodes.as<float4>(), static_cast<uint32_t>(ctx->n_pnodes), ctx->grid_spacing.as<float>(), ctx->stream));
+  std::vector<float> sp(m);
+  double bounds[6], centre[4];
+  CU(cudaMemcpyAsync(sp.data(), ctx->grid_spacing.p, m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(bounds, ctx->tgt_bounds.p, sizeof(bounds), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(centre, ctx->tgt_centre.p, sizeof(centre), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  size_t k = 0;
+  for (size_t i = 0; i < m; i++)
+    if (sp[i] > 0.f) sp[k++] = sp[i];
+  if (k == 0) return 0;
+  std::nth_element(sp.begin(), sp.begin() + k / 2, sp.begin() + k);
+  double cell_factor = 3.0;  // cell edge in units of the median point spacing
+  if (const char* e = std::getenv("SGB_GRID_CELL")) {  // profiling switch
+    const double v = std::atof(e);
+    if (v > 0.1 && v < 100.0) cell_factor = v;
+  }
+  double cell = cell_factor * sp[k / 2];
+  double ext = 0.0;
+  for (int a = 0; a < 3; a++) ext = std::max(ext, bounds[3 + a] - bounds[a]);
+  if (!(cell > 0.0) || !(ext > 0.0)) return 0;
+  cell = std::max(cell, ext / 500000.0);  // 21-bit cell coordinates with room for queries outside the box
+  GridParams g;
+  for (int a = 0; a < 3; a++) g.origin[a] = static_cast<float>(bounds[a] - centre[a]);
+  g.inv_cell = static_cast<float>(1.0 / cell);
+  const double settle = 0.5 * cell * (1.0 - 4e-3);  // margin for the FP32 cell-coordinate arithmetic
+  g.settle_d2 = static_cast<float>(settle * settle);
+  uint32_t capacity = 1024;
+  while (capacity < 2 * n) capacity <<= 1;
+  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_vals_out.reserve(n * sizeof(uint32_t)));
+  CU(ctx->grid_pts.reserve(n * sizeof(float4)));
+  CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
+  size_t tb = 0;
+  CU(sort_pairs_u64_u32(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), n,
+                        ctx->stream));
+  CU(ctx->sort_temp.reserve(tb));
+  CU(launch_grid_build(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                       ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->stream));
+  ctx->launches += 8;
+  for (int a = 0; a < 3; a++) ctx->grid_origin[a] = g.origin[a];
+  ctx->grid_inv_cell = g.inv_cell;
+  ctx->grid_settle_d2 = g.settle_d2;
+  ctx->grid_cell = static_cast<float>(cell);
+  ctx->grid_capacity = capacity;
+  ctx->grid_ready = true;
   return 0;
 }
 

@@ -56,6 +56,12 @@ struct sgb_ctx {
   bool host_tree = false;   // profiling switch: sgb_target_build_kdtree builds a median-split kd-tree on the host
   int tree_quality = 1;     // device construction: 1 = Hilbert order + per-level median-split refinement (kd quality), 0 = Hilbert order only (linear BVH)
   sgb::DevBuf pre_boxes;
+  size_t n_pnodes = 0;      // packet records of the current target tree
+  // uniform-grid front end of the search (sgb_grid.cu)
+  bool use_grid = true, grid_ready = false;
+  sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0] = count, [1..] = pending query positions
+  uint32_t grid_capacity = 0;
+  float grid_origin[3] = {0, 0, 0}, grid_inv_cell = 1.f, grid_settle_d2 = 0.f, grid_cell = 0.f;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;
   uint32_t vox_mask = 0;
@@ -96,6 +102,8 @@ inline int fail(sgb_ctx* c, int code, const std::string& msg) {
 
 /// device-side tree construction (sgb_capi_preprocess.cu)
 int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d_centre4, DevBuf& perm, DevBuf& leaf_pts, DevBuf& pnodes, int* depth);
+/// uniform grid over the current (leaf-ordered) target for the search front end; no-op unless enabled
+int build_grid(sgb_ctx* ctx);
 
 }  // namespace sgb
 

@@ -30,7 +30,25 @@ cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t*
 
 // sgb_kernels_packet.cu
 int packet_occupancy(int max_depth);
-cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, cudaStream_t st);
+cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
+                                 uint32_t min_pending, cudaStream_t st);
+// sgb_grid.cu: uniform-grid front end of the search
+struct GridParams {
+  float origin[3];  // minimum corner of the target's box (centred frame)
+  float inv_cell;   // 1 / cell edge
+  float settle_d2;  // a candidate within this squared distance is provably the nearest neighbour ((cell/2 - margin)^2)
+};
+struct __align__(16) GridSlot {
+  unsigned long long key;  // packed cell coordinates, ~0 = empty
+  uint32_t start, count;   // run of the cell's points in the cell-ordered copy of the target
+};
+cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* out, cudaStream_t st);
+cudaError_t launch_grid_build(const float4* leaf_pts, uint32_t n, const GridParams& g, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
+                              void* sort_temp, size_t sort_temp_bytes, float4* grid_pts, GridSlot* table, uint32_t capacity, cudaStream_t st);
+cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, uint8_t* state,
+                              uint32_t* pending_count, uint32_t* pending_list, cudaStream_t st);
+cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
+                                  uint32_t max_pending, int grid, cudaStream_t st);
 // device-side tree construction (sgb_kernels.cu)
 constexpr uint32_t kLbvhLeafPoints = 32;
 cudaError_t launch_curve_keys(const float4* pts, size_t n, const double* centre4, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);

@@ -31,7 +31,12 @@ __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const f
   return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth) {
+__global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
+                                                                  const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
+                                                                  uint32_t min_pending) {
+  // with the grid front end this kernel only runs when MANY queries are pending (misaligned first iterations); a handful
+  // of scattered pending queries is served by pending_search_kernel instead
+  if (pending_count && *pending_count <= min_pending) return;
   extern __shared__ float s_dist[];  // [max_depth][kLinBlock] per-lane box distance of each pending subtree
   __shared__ uint2 s_child[kPktWarps][40];  // per-warp: the pending subtrees themselves (warp-uniform)
   const double* R = P.T;
@@ -48,7 +53,10 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
 
   for (uint32_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
     const uint32_t i = chunk * 32u + lane;
-    const bool valid = i < P.src.n;
+    // with the grid front end (sgb_grid.cu) most queries are already settled; only the pending ones walk the tree,
+    // seeded with the candidate the grid probe left in corr[]
+    const bool valid = i < P.src.n && !(settled && settled[i]);
+    if (!__any_sync(0xffffffffu, valid)) continue;
     float fx = 0.f, fy = 0.f, fz = 0.f;
     float best_d = -1.0f;  // an idle lane is never interested in anything
     uint32_t best = kNone;
@@ -59,7 +67,7 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
       fy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
       fz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
       best_d = P.max_dist_sq;
-      const uint32_t prev = P.use_prev ? P.corr[i] : kNone;  // seed: an upper bound only prunes
+      const uint32_t prev = (P.use_prev || settled) ? P.corr[i] : kNone;  // seed: an upper bound only prunes
       if (prev != kNone) {
         const float4 t = __ldg(&pts[prev]);
         const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
@@ -193,10 +201,11 @@ int packet_occupancy(int max_depth) {
   return nb > 0 ? nb : 1;
 }
 
-cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, cudaStream_t st) {
+cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
+                                 uint32_t min_pending, cudaStream_t st) {
   if (max_depth > 40) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
-  packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth);
+  packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending);
   return cudaGetLastError();
 }
 
