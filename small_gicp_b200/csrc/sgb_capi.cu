@@ -2,9 +2,11 @@
 // Context + C-ABI (include/sgicp_b200.h) of the B200-native small_gicp hot path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -161,7 +163,9 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
       if (sgrid > scap) sgrid = scap;
       const uint8_t* settled = nullptr;
       const uint32_t* pending_count = nullptr;
-      const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / 8);  // more pending than this: warp-cooperative search, else per-thread
+      // more pending queries than this: packet search over the chunk-ordered queries, else a warp per pending query
+      static const int split_div = std::getenv("SGB_PENDING_DIV") ? std::max(1, std::atoi(std::getenv("SGB_PENDING_DIV"))) : 16;  // profiling switch
+      const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / split_div);
       if (ctx->grid_ready) {
         // grid front end: settles every query whose nearest neighbour lies within half a cell (sgb_grid.cu)
         CU(ctx->grid_state.reserve(ctx->n_src));
@@ -169,11 +173,22 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
         for (int a = 0; a < 3; a++) g.origin[a] = ctx->grid_origin[a];
         g.inv_cell = ctx->grid_inv_cell;
         g.settle_d2 = ctx->grid_settle_d2;
-        CU(ctx->grid_pending.reserve((ctx->n_src + 1) * sizeof(uint32_t)));
-        uint32_t* pc = ctx->grid_pending.as<uint32_t>();
-        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_state.as<uint8_t>(), pc, pc + 1,
-                             ctx->stream));
-        CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, pc + 1, pending_split, ctx->sm_count * 4, ctx->stream));
+        // [0], [1]: two pending counters that alternate between calls (each probe clears the other one), [2..]: the list
+        const void* before = ctx->grid_pending.p;
+        CU(ctx->grid_pending.reserve((ctx->n_src + 2) * sizeof(uint32_t)));
+        if (ctx->grid_pending.p != before || !ctx->pending_clean) {
+          CU(cudaMemsetAsync(ctx->grid_pending.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+          ctx->pending_clean = true;
+        }
+        uint32_t* pbase = ctx->grid_pending.as<uint32_t>();
+        uint32_t* pc = pbase + ctx->pending_parity;
+        uint32_t* plist = pbase + 2;
+        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->grid_state.as<uint8_t>(), pc,
+                             plist, pbase + (ctx->pending_parity ^ 1), ctx->stream));
+        ctx->pending_parity ^= 1;
+        static const bool ring = !(std::getenv("SGB_RING") && std::atoi(std::getenv("SGB_RING")) == 0);  // profiling switch
+        CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, plist, pending_split, ctx->grid_pts.as<float4>(),
+                                 (ctx->grid_blocks && ring) ? ctx->grid_table.as<GridSlot>() : nullptr, ctx->grid_capacity, g, ctx->sm_count * 8, ctx->stream));
         ctx->launches += 2;
         settled = ctx->grid_state.as<uint8_t>();
         pending_count = pc;
@@ -191,8 +206,12 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
       if (sgrid > scap) sgrid = scap;
       CU(launch_search(P, sgrid, depth, ctx->stream));
     }
+    // exactly one wave of the factor kernel (its CTAs loop over tiles)
     int fgrid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
-    if (fgrid > grid) fgrid = grid;
+    const int fcap = ctx->sm_count * factor_reduce_occupancy(factor, robust);
+    if (fgrid > fcap) fgrid = fcap;
+    if (int rc = ensure_reduction_buffers(ctx, fgrid)) return rc;
+    P.partials = ctx->partials.as<double>();
     CU(launch_factor_reduce(P, factor, robust, fgrid, ctx->stream));
     ctx->launches += 2;
   } else {

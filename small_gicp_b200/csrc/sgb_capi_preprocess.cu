@@ -99,27 +99,40 @@ int build_grid(sgb_ctx* ctx) {
   double ext = 0.0;
   for (int a = 0; a < 3; a++) ext = std::max(ext, bounds[3 + a] - bounds[a]);
   if (!(cell > 0.0) || !(ext > 0.0)) return 0;
-  cell = std::max(cell, ext / 500000.0);  // 21-bit cell coordinates with room for queries outside the box
+  cell = std::max(cell, ext / 8000.0);  // cell indices < 2^13: FP32 cell coordinates stay accurate to 1e-3 cells (kGridSlack in sgb_grid.cu)
   GridParams g;
   for (int a = 0; a < 3; a++) g.origin[a] = static_cast<float>(bounds[a] - centre[a]);
   g.inv_cell = static_cast<float>(1.0 / cell);
-  const double settle = 0.5 * cell * (1.0 - 4e-3);  // margin for the FP32 cell-coordinate arithmetic
+  const double settle = (0.5 - 4e-3) * cell;  // margin for the FP32 cell-coordinate arithmetic (kGridSlack cells, sgb_grid.cu)
   g.settle_d2 = static_cast<float>(settle * settle);
-  uint32_t capacity = 1024;
-  while (capacity < 2 * n) capacity <<= 1;
-  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
-  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
-  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
-  CU(ctx->pre_vals_out.reserve(n * sizeof(uint32_t)));
-  CU(ctx->grid_pts.reserve(n * sizeof(float4)));
-  CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
+  static const bool blocks_env = !(std::getenv("SGB_GRID_BLOCKS") && std::atoi(std::getenv("SGB_GRID_BLOCKS")) == 0);  // profiling switch
+  const bool blocks = blocks_env;
+  const size_t n_ent = blocks ? n * 8 : n;  // block lists hold every point under its eight enclosing 2 x 2 x 2 blocks
+  if (n_ent >= (1ull << 31)) return 0;
+  CU(ctx->keys_in.reserve(n_ent * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n_ent * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n_ent * sizeof(uint32_t)));
+  CU(ctx->pre_vals_out.reserve(n_ent * sizeof(uint32_t)));
+  CU(ctx->grid_pts.reserve(n_ent * sizeof(float4)));
+  CU(ctx->grid_pending.reserve(sizeof(uint32_t)));
   size_t tb = 0;
-  CU(sort_pairs_u64_u32(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), n,
+  CU(sort_pairs_u64_u32(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), n_ent,
                         ctx->stream));
   CU(ctx->sort_temp.reserve(tb));
-  CU(launch_grid_build(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
-                       ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->stream));
-  ctx->launches += 8;
+  uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the pending counter doubles as scratch during construction
+  CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, blocks, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+                      ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->stream));
+  uint32_t distinct = 0;
+  CU(cudaMemcpyAsync(&distinct, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  uint32_t capacity = 1024;
+  while (capacity < 2ull * distinct) capacity <<= 1;  // load factor <= 1/2
+  CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
+  CU(launch_grid_fill(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n_ent),
+                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->stream));
+  ctx->grid_blocks = blocks;
+  ctx->pending_clean = false;  // d_distinct lives in the first pending counter
+  ctx->launches += 9;
   for (int a = 0; a < 3; a++) ctx->grid_origin[a] = g.origin[a];
   ctx->grid_inv_cell = g.inv_cell;
   ctx->grid_settle_d2 = g.settle_d2;

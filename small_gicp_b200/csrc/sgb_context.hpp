@@ -58,9 +58,11 @@ struct sgb_ctx {
   sgb::DevBuf pre_boxes;
   size_t n_pnodes = 0;      // packet records of the current target tree
   // uniform-grid front end of the search (sgb_grid.cu)
-  bool use_grid = true, grid_ready = false;
+  bool use_grid = true, grid_ready = false, grid_blocks = true;  // grid_blocks: 2 x 2 x 2 block lists (one lookup per query) instead of per-cell lists
   sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0] = count, [1..] = pending query positions
   uint32_t grid_capacity = 0;
+  bool pending_clean = false;  // both pending counters are zero / maintained by the probe kernels
+  int pending_parity = 0;
   float grid_origin[3] = {0, 0, 0}, grid_inv_cell = 1.f, grid_settle_d2 = 0.f, grid_cell = 0.f;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;

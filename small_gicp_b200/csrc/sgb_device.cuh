@@ -268,9 +268,24 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // The whole CTA adds the partials (a single thread per sum chasing gridDim.x L2 round trips left every other SM idle
+  // for ~25 us, profiles/r01/p): warp g sums CTAs g, g + W, g + 2W, ... with several loads in flight, then the W
+  // group sums are added in group order.  The order is fixed by (gridDim.x, W) alone, so the result is deterministic.
+  {
+    constexpr int W = kLinBlock / 32;
+    static_assert(NACC <= 32, "one lane per accumulator");
+    double v = 0.0;
+    if (lane < NACC) {
+#pragma unroll 8
+      for (unsigned int b = warp; b < gridDim.x; b += W) v += __ldcg(&partials[static_cast<size_t>(b) * kPartialStride + lane]);
+      s_red[warp][lane] = v;
+    }
+  }
+  __syncthreads();
   if (threadIdx.x < NACC) {
     double v = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; b++) v += __ldcg(&partials[static_cast<size_t>(b) * kPartialStride + threadIdx.x]);
+#pragma unroll
+    for (int w = 0; w < kLinBlock / 32; w++) v += s_red[w][threadIdx.x];
     if (!EXPAND) {
       out[threadIdx.x] = v;
     } else {

@@ -4,12 +4,16 @@
 // In a registration that is not wildly misaligned almost every query's nearest neighbour is a fraction of the point
 // spacing away.  For such a query a hash probe of the 2 x 2 x 2 block of grid cells (cell edge c) that covers the cube
 // [q - c/2, q + c/2]^3 sees EVERY target point within c/2 of q, so if the closest point found is within c/2 it is the
-// exact nearest neighbour and the query is finished: 8 independent loads + a few dozen distance tests, no tree walk,
-// no dependent pointer chasing.  Queries it cannot settle (nothing within c/2: misaligned first iterations, holes,
-// outliers) are left pending -- with the best candidate found so far as an upper bound -- for the packet tree search
-// (sgb_kernels_packet.cu), which still returns exact results for them.  Results are therefore identical to a pure tree
-// search (exact ties aside); ncu evidence and the A/B switch (SGB_GRID=0) are recorded in profiles/.
+// exact nearest neighbour and the query is finished: a hash lookup or three + a few dozen distance tests, no tree walk,
+// no dependent pointer chasing.  The query's own cell is scanned first; each of the other seven cells of the block is
+// looked up only if its box is still closer than the best distance so far (usually one or two are).
+// Queries it cannot settle (nothing within c/2: misaligned first iterations, holes, outliers) are appended to a compact
+// pending list -- with the best candidate found so far as an upper bound -- and finished exactly by a tree search:
+// a warp per pending query when they are few (pending_search_kernel below), the packet search (sgb_kernels_packet.cu)
+// when they are many.  Results are therefore identical to a pure tree search (exact ties aside); ncu evidence and the
+// A/B switch (SGB_GRID=0) are recorded in profiles/.
 #include <cfloat>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sgb_device.cuh"
@@ -17,28 +21,46 @@
 
 namespace sgb {
 
+// slack (in cells) for the FP32 cell-coordinate arithmetic: cell indices stay below 2^13 (build_grid), so a coordinate
+// in cell units carries < 1e-3 of rounding error
+constexpr float kGridSlack = 4e-3f;
+
 __device__ __forceinline__ uint64_t grid_key(int ix, int iy, int iz) {
   return (static_cast<uint64_t>(static_cast<uint32_t>(ix + (1 << 20)) & 0x1fffffu)) | (static_cast<uint64_t>(static_cast<uint32_t>(iy + (1 << 20)) & 0x1fffffu) << 21) |
          (static_cast<uint64_t>(static_cast<uint32_t>(iz + (1 << 20)) & 0x1fffffu) << 42);
 }
-__device__ __forceinline__ uint32_t grid_hash(uint64_t k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return static_cast<uint32_t>(k);
+__device__ __forceinline__ uint32_t grid_hash(int ix, int iy, int iz) {
+  uint32_t h = static_cast<uint32_t>(ix) * 73856093u ^ static_cast<uint32_t>(iy) * 19349663u ^ static_cast<uint32_t>(iz) * 83492791u;
+  h ^= h >> 15;
+  return h;
+}
+__device__ __forceinline__ uint32_t grid_hash_of_key(uint64_t k) {
+  const int ix = static_cast<int>(k & 0x1fffffu) - (1 << 20), iy = static_cast<int>((k >> 21) & 0x1fffffu) - (1 << 20),
+            iz = static_cast<int>((k >> 42) & 0x1fffffu) - (1 << 20);
+  return grid_hash(ix, iy, iz);
 }
 
-// cell key of every target point (leaf-ordered, centred FP32); value = leaf position
+// cell key of every target point (leaf-ordered, centred FP32); value = leaf position.
+// BLOCKS: every point is entered under the eight 2 x 2 x 2 cell blocks that contain its cell (block anchor = lowest cell),
+// so that a query finds every point of the block around it in ONE contiguous run (8x the points, one lookup, one loop).
+template <bool BLOCKS>
 __global__ void grid_keys_kernel(const float4* __restrict__ pts, uint32_t n, GridParams g, uint64_t* keys, uint32_t* vals) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = BLOCKS ? t >> 3 : t, o = BLOCKS ? t & 7u : 0u;
   if (i >= n) return;
   const float4 p = pts[i];
   const int ix = __float2int_rd((p.x - g.origin[0]) * g.inv_cell), iy = __float2int_rd((p.y - g.origin[1]) * g.inv_cell),
             iz = __float2int_rd((p.z - g.origin[2]) * g.inv_cell);
-  keys[i] = grid_key(ix, iy, iz);
-  vals[i] = i;
+  keys[t] = grid_key(ix - static_cast<int>(o & 1u), iy - static_cast<int>((o >> 1) & 1u), iz - static_cast<int>(o >> 2));
+  vals[t] = i;
+}
+
+// number of distinct keys of the sorted key array (sizes the hash table)
+__global__ void grid_count_heads_kernel(const uint64_t* __restrict__ keys, uint32_t m, uint32_t* count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool head = i < m && (i == 0 || keys[i - 1] != keys[i]);
+  const unsigned b = __ballot_sync(0xffffffffu, head);
+  if ((threadIdx.x & 31u) == 0 && b) atomicAdd(count, static_cast<uint32_t>(__popc(b)));
 }
 
 // after the sort: gather the points into cell order (w = leaf position) and insert one table entry per run of equal keys
@@ -53,7 +75,7 @@ __global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32
   if (i == 0 || keys[i - 1] != k) {  // head of a cell: count its points, claim a slot
     uint32_t cnt = 1;
     while (i + cnt < n && keys[i + cnt] == k) cnt++;
-    uint32_t slot = grid_hash(k) & mask;
+    uint32_t slot = grid_hash_of_key(k) & mask;
     for (;;) {
       const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), ~0ull, static_cast<unsigned long long>(k));
       if (prev == ~0ull) break;
@@ -73,15 +95,42 @@ __global__ void grid_table_init_kernel(GridSlot* table, uint32_t capacity) {
   }
 }
 
+__device__ __forceinline__ uint2 grid_lookup(const GridSlot* __restrict__ table, uint32_t mask, int ix, int iy, int iz) {
+  const uint64_t k = grid_key(ix, iy, iz);
+  uint32_t slot = grid_hash(ix, iy, iz) & mask;
+  for (;;) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&table[slot]));
+    const uint64_t ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
+    if (ek == k) return make_uint2(e.z, e.w);
+    if (ek == ~0ull) return make_uint2(0u, 0u);
+    slot = (slot + 1u) & mask;
+  }
+}
+
+__device__ __forceinline__ void grid_scan(const float4* __restrict__ cp, uint32_t cnt, float fx, float fy, float fz, float& best_d, uint32_t& best) {
+#pragma unroll 4
+  for (uint32_t j = 0; j < cnt; j++) {
+    const float4 t = __ldg(&cp[j]);
+    const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+    const float d = dx * dx + dy * dy + dz * dz;
+    if (d < best_d) {
+      best_d = d;
+      best = __float_as_uint(t.w);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // probe: one query per thread (Hilbert order -> neighbouring lanes hit neighbouring cells)
-// state[i] = 1: settled (corr[i] is the exact nearest neighbour or kNone is impossible here), 0: pending for the tree search
+// state[i] = 1: settled (corr[i] is the exact nearest neighbour), 0: pending for the tree search (corr[i] = best candidate)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_probe_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
-                                                        const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
-                                                        uint32_t* pending_count, uint32_t* pending_list) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
+                                                           const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell_sq, uint8_t* state,
+                                                           uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = gi < P.src.n;
+  if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
   const uint32_t i = in_range ? gi : P.src.n - 1u;  // out-of-range lanes shadow the last query (no divergent exit before the warp vote below)
   const double* R = P.T;
   const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
@@ -96,32 +145,107 @@ __global__ void __launch_bounds__(256) grid_probe_kernel(const __grid_constant__
 
   float best_d = P.max_dist_sq;
   uint32_t best = kNone;
-  // the 2 x 2 x 2 block covering [q - c/2, q + c/2]^3
-  const int bx = __float2int_rd((fx - g.origin[0]) * g.inv_cell - 0.5f), by = __float2int_rd((fy - g.origin[1]) * g.inv_cell - 0.5f),
-            bz = __float2int_rd((fz - g.origin[2]) * g.inv_cell - 0.5f);
-  uint32_t starts[8], counts[8];
+  // own cell, and per axis the neighbour on the side the query leans to: together the 2 x 2 x 2 block around [q - c/2, q + c/2]^3
+  const float ux = (fx - g.origin[0]) * g.inv_cell, uy = (fy - g.origin[1]) * g.inv_cell, uz = (fz - g.origin[2]) * g.inv_cell;
+  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+  // queries far outside the target's box cannot be settled anyway; clamping keeps the integer cell coordinates in range
+  const int ox = static_cast<int>(fminf(fmaxf(flx, -1e5f), 1e5f)), oy = static_cast<int>(fminf(fmaxf(fly, -1e5f), 1e5f)),
+            oz = static_cast<int>(fminf(fmaxf(flz, -1e5f), 1e5f));
+  const float frx = ux - flx, fry = uy - fly, frz = uz - flz;
+  const int nx = frx >= 0.5f ? 1 : -1, ny = fry >= 0.5f ? 1 : -1, nz = frz >= 0.5f ? 1 : -1;
+  // squared distance (cell units, less the rounding slack) to the neighbour cell's slab along each axis
+  const float ax = fmaxf((frx >= 0.5f ? 1.0f - frx : frx) - kGridSlack, 0.0f), ay = fmaxf((fry >= 0.5f ? 1.0f - fry : fry) - kGridSlack, 0.0f),
+              az = fmaxf((frz >= 0.5f ? 1.0f - frz : frz) - kGridSlack, 0.0f);
+  const float ax2 = ax * ax * cell_sq, ay2 = ay * ay * cell_sq, az2 = az * az * cell_sq;
+  // all eight table lookups first: eight independent loads in flight, no divergence (the first slot of each probe
+  // sequence is fetched unconditionally; collisions are resolved below)
+  uint4 ent[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    const uint64_t k = grid_key(bx + (c & 1), by + ((c >> 1) & 1), bz + (c >> 2));
-    uint32_t slot = grid_hash(k) & mask;
-    uint32_t st = 0, cn = 0;
-    for (;;) {
-      const GridSlot e = table[slot];
-      if (e.key == k) {
-        st = e.start;
-        cn = e.count;
-        break;
-      }
-      if (e.key == ~0ull) break;
-      slot = (slot + 1u) & mask;
-    }
-    starts[c] = st;
-    counts[c] = cn;
+    const int ix = ox + ((c & 1) ? nx : 0), iy = oy + ((c & 2) ? ny : 0), iz = oz + ((c & 4) ? nz : 0);
+    ent[c] = __ldg(reinterpret_cast<const uint4*>(&table[grid_hash(ix, iy, iz) & mask]));
   }
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    const float4* cp = grid_pts + starts[c];
-    for (uint32_t j = 0; j < counts[c]; j++) {
+    // the own cell first, then the neighbours whose box is still closer than the best distance so far
+    const float bd = ((c & 1) ? ax2 : 0.f) + ((c & 2) ? ay2 : 0.f) + ((c & 4) ? az2 : 0.f);
+    if (!(bd < best_d)) continue;
+    const int ix = ox + ((c & 1) ? nx : 0), iy = oy + ((c & 2) ? ny : 0), iz = oz + ((c & 4) ? nz : 0);
+    const uint64_t key = grid_key(ix, iy, iz);
+    uint4 e = ent[c];
+    uint64_t ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
+    uint32_t slot = grid_hash(ix, iy, iz) & mask;
+    while (ek != key && ek != ~0ull) {  // rare: the table is sparsely filled
+      slot = (slot + 1u) & mask;
+      e = __ldg(reinterpret_cast<const uint4*>(&table[slot]));
+      ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
+    }
+    if (ek == key) grid_scan(grid_pts + e.z, e.w, fx, fy, fz, best_d, best);
+  }
+  const bool settled = best != kNone && best_d <= g.settle_d2;
+  if (!settled && P.use_prev) {  // keep the better of (grid candidate, previous correspondence) as the tree search's seed
+    const uint32_t prev = P.corr[i];
+    if (prev != kNone && best == kNone) best = prev;
+    else if (prev != kNone) {
+      const float4 t = __ldg(&P.tgt.pts[prev]);
+      const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+      if (dx * dx + dy * dy + dz * dz < best_d) best = prev;
+    }
+  }
+  if (in_range) {
+    P.corr[i] = best;
+    state[i] = settled ? 1 : 0;
+  }
+  // pending queries go to a compact work list (warp-aggregated append)
+  const bool pend = in_range && !settled;
+  const unsigned m = __ballot_sync(0xffffffffu, pend);
+  if (m) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == static_cast<uint32_t>(__ffs(m) - 1)) base = atomicAdd(pending_count, static_cast<uint32_t>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pend) pending_list[base + __popc(m & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
+                                                               const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
+                                                               uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
+  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = gi < P.src.n;
+  if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
+  const uint32_t i = in_range ? gi : P.src.n - 1u;
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
+  const float4 s = __ldg(&P.src.pts[i]);
+  const double sx = s.x, sy = s.y, sz = s.z;
+  const float fx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
+  const float fy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
+  const float fz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
+  float best_d = P.max_dist_sq;
+  uint32_t best = kNone;
+  const float ax = floorf((fx - g.origin[0]) * g.inv_cell - 0.5f), ay = floorf((fy - g.origin[1]) * g.inv_cell - 0.5f),
+              az = floorf((fz - g.origin[2]) * g.inv_cell - 0.5f);
+  // queries far outside the target's box cannot be settled anyway; clamping keeps the integer cell coordinates in range
+  const int bx = static_cast<int>(fminf(fmaxf(ax, -1e5f), 1e5f)), by = static_cast<int>(fminf(fmaxf(ay, -1e5f), 1e5f)),
+            bz = static_cast<int>(fminf(fmaxf(az, -1e5f), 1e5f));
+  const uint2 e = grid_lookup(table, mask, bx, by, bz);
+  {
+    // the list is a contiguous run of e.y points: pull all of its lines into L2 at once (the scan below would otherwise
+    // pay one DRAM round trip per batch of loads: profiles/r01/q, 29 warps stalled on the scoreboard per issue)
+    const char* lp = reinterpret_cast<const char*>(grid_pts + e.x);
+    const uint32_t bytes = e.y * 16u;
+    for (uint32_t off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + off));
+    if (bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + bytes - 16u));  // last line of a run that is not 128 B aligned
+    const float4* __restrict__ cp = grid_pts + e.x;
+#pragma unroll 8
+    for (uint32_t j = 0; j < e.y; j++) {
       const float4 t = __ldg(&cp[j]);
       const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
       const float d = dx * dx + dy * dy + dz * dz;
@@ -145,7 +269,6 @@ __global__ void __launch_bounds__(256) grid_probe_kernel(const __grid_constant__
     P.corr[i] = best;
     state[i] = settled ? 1 : 0;
   }
-  // pending queries go to a compact work list (warp-aggregated append) for the per-thread tree search
   const bool pend = in_range && !settled;
   const unsigned m = __ballot_sync(0xffffffffu, pend);
   if (m) {
@@ -158,9 +281,15 @@ __global__ void __launch_bounds__(256) grid_probe_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Pending queries (a few per cent, scattered): exact NN by an individual walk of the packet records, seeded with the
-// candidate left in corr[].  Skipped (the warp-cooperative search runs instead) when more than `max_pending` are pending.
+// Few pending queries (holes, outliers, borders: a few per cent, scattered): one WARP per query walks the packet
+// records.  Every step of a single walk is a dependent load, so a thread per query would be pure latency (measured:
+// 300 us for 1000 queries); with a warp per query a leaf's points are fetched by one coalesced load and reduced by a
+// hardware min, and thousands of walks are in flight at once.  Skipped -- the packet search handles the chunk-ordered
+// queries instead -- when more than `max_pending` queries are pending.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kPendWarps = kLinBlock / 32;
+constexpr int kPendStack = 40;
+
 __device__ __forceinline__ float grid_box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
   const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
   const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
@@ -168,22 +297,26 @@ __device__ __forceinline__ float grid_box_dist2(float qx, float qy, float qz, co
   return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int depth,
+__global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes,
                                                                    const uint32_t* __restrict__ pending_count, const uint32_t* __restrict__ pending_list,
-                                                                   uint32_t max_pending) {
-  extern __shared__ uint2 s_desc[];  // [depth][kLinBlock] descriptors, then [depth][kLinBlock] box distances
+                                                                   uint32_t max_pending, const float4* __restrict__ grid_pts,
+                                                                   const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell) {
+  __shared__ uint2 s_desc[kPendWarps][kPendStack];
+  __shared__ float s_dist[kPendWarps][kPendStack];
   const uint32_t count = *pending_count;
   if (count > max_pending) return;
-  float* s_dist = reinterpret_cast<float*>(s_desc + static_cast<size_t>(depth) * kLinBlock);
-  uint2* my_desc = s_desc + threadIdx.x;
-  float* my_dist = s_dist + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  uint2* desc = s_desc[wib];
+  float* dist = s_dist[wib];
   const double* R = P.T;
   const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
   const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
   const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
   const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
   const float4* __restrict__ pts = P.tgt.pts;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+  for (uint32_t k = warp; k < count; k += n_warps) {
+    // everything below is warp-uniform except the leaf scan
     const uint32_t i = pending_list[k];
     const float4 s = __ldg(&P.src.pts[i]);
     const double sx = s.x, sy = s.y, sz = s.z;
@@ -202,6 +335,38 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
         best = seed;
       }
     }
+    if (table) {
+      // Ring phase (block lists): the 3 x 3 x 3 blocks at stride 2 around the query's own block tile the cells
+      // [a - 2, a + 4)^3, i.e. they hold every target point within 2.5 cells of q.  One lookup and one list scan per lane,
+      // all 27 in parallel, then a warp min: a handful of memory round trips instead of the ~45 of a tree walk.
+      const float ux = (qx - g.origin[0]) * g.inv_cell, uy = (qy - g.origin[1]) * g.inv_cell, uz = (qz - g.origin[2]) * g.inv_cell;
+      const int ax = static_cast<int>(fminf(fmaxf(floorf(ux - 0.5f), -1e5f), 1e5f)), ay = static_cast<int>(fminf(fmaxf(floorf(uy - 0.5f), -1e5f), 1e5f)),
+                az = static_cast<int>(fminf(fmaxf(floorf(uz - 0.5f), -1e5f), 1e5f));
+      uint2 e = make_uint2(0u, 0u);
+      if (lane < 27u) {
+        const int bx = ax + 2 * (static_cast<int>(lane % 3u) - 1), by = ay + 2 * (static_cast<int>((lane / 3u) % 3u) - 1),
+                  bz = az + 2 * (static_cast<int>(lane / 9u) - 1);
+        const float ex = fmaxf(fmaxf(static_cast<float>(bx) - ux, ux - static_cast<float>(bx + 2)) - kGridSlack, 0.0f);
+        const float ey = fmaxf(fmaxf(static_cast<float>(by) - uy, uy - static_cast<float>(by + 2)) - kGridSlack, 0.0f);
+        const float ez = fmaxf(fmaxf(static_cast<float>(bz) - uz, uz - static_cast<float>(bz + 2)) - kGridSlack, 0.0f);
+        if ((ex * ex + ey * ey + ez * ez) * cell * cell < best_d) e = grid_lookup(table, mask, bx, by, bz);
+      }
+      float my_d = best_d;
+      uint32_t my_best = kNone;
+      grid_scan(grid_pts + e.x, e.y, qx, qy, qz, my_d, my_best);
+      const uint32_t dbits = my_best != kNone ? __float_as_uint(my_d) : 0x7f800000u;
+      const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
+      if (dmin != 0x7f800000u) {
+        const unsigned who = __ballot_sync(0xffffffffu, dbits == dmin);
+        best = __shfl_sync(0xffffffffu, my_best, __ffs(who) - 1);
+        best_d = __uint_as_float(dmin);
+      }
+      const float cover = (2.5f - kGridSlack) * cell;
+      if (best_d <= cover * cover) {  // everything within sqrt(best_d) of q has been examined: exact (or exactly nothing)
+        if (lane == 0) P.corr[i] = best;
+        continue;
+      }
+    }
     int sp = 0;
     uint32_t cur = 0;
     bool expand = true;
@@ -213,11 +378,13 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
         const float dl = grid_box_dist2(qx, qy, qz, n0, n1), dr = grid_box_dist2(qx, qy, qz, n2, n3);
         const bool left_first = dl <= dr;
         const float dn = left_first ? dl : dr, df = left_first ? dr : dl;
-        const uint2 cn = left_first ? make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w)) : make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w));
-        const uint2 cf = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
-        if (df < best_d) {
-          my_desc[sp * kLinBlock] = cf;
-          my_dist[sp * kLinBlock] = df;
+        const uint2 cl = make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w)), cr = make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w));
+        const uint2 cn = left_first ? cl : cr, cf = left_first ? cr : cl;
+        if (df < best_d && sp < kPendStack) {
+          if (lane == 0) {
+            desc[sp] = cf;
+            dist[sp] = df;
+          }
           sp++;
         }
         if (!(dn < best_d)) {
@@ -231,14 +398,16 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
         leaf = cn;
       } else {
         bool got = false;
+        __syncwarp();
         while (sp > 0) {
           sp--;
-          if (my_dist[sp * kLinBlock] < best_d) {
-            leaf = my_desc[sp * kLinBlock];
+          if (dist[sp] < best_d) {
+            leaf = desc[sp];
             got = true;
             break;
           }
         }
+        __syncwarp();
         if (!got) break;
         if (leaf.y == 0u) {
           cur = leaf.x;
@@ -246,18 +415,26 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
           continue;
         }
       }
-      for (uint32_t j = 0; j < leaf.y; j++) {
-        const float4 t = __ldg(&pts[leaf.x + j]);
-        const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-        const float d = dx * dx + dy * dy + dz * dz;
+      // leaf: lane j takes point j, the nearest comes out of one hardware min (non-negative floats order like their bits)
+      for (uint32_t base = 0; base < leaf.y; base += 32u) {
+        const uint32_t j = base + lane;
+        uint32_t dbits = 0x7f800000u;
+        if (j < leaf.y) {
+          const float4 t = __ldg(&pts[leaf.x + j]);
+          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+          dbits = __float_as_uint(dx * dx + dy * dy + dz * dz);
+        }
+        const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
+        const float d = __uint_as_float(dmin);
         if (d < best_d) {
+          const unsigned who = __ballot_sync(0xffffffffu, dbits == dmin);  // lowest lane = first point in scan order
           best_d = d;
-          best = leaf.x + j;
+          best = leaf.x + base + (__ffs(who) - 1);
         }
       }
       expand = false;
     }
-    P.corr[i] = best;
+    if (lane == 0) P.corr[i] = best;
   }
 }
 
@@ -284,33 +461,47 @@ cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* o
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_build(const float4* leaf_pts, uint32_t n, const GridParams& g, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
-                              void* sort_temp, size_t sort_temp_bytes, float4* grid_pts, GridSlot* table, uint32_t capacity, cudaStream_t st) {
-  grid_keys_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in);
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0, 63, st);
+cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
+                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, cudaStream_t st) {
+  const uint32_t m = blocks ? n * 8u : n;
+  if (blocks)
+    grid_keys_kernel<true><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in);
+  else
+    grid_keys_kernel<false><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(m), 0, 63, st);
   if (e != cudaSuccess) return e;
-  grid_table_init_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
-  grid_fill_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(keys_out, vals_out, leaf_pts, n, grid_pts, table, capacity - 1u);
+  e = cudaMemsetAsync(d_distinct, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  grid_count_heads_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_out, m, d_distinct);
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, uint8_t* state,
-                              uint32_t* pending_count, uint32_t* pending_list, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(pending_count, 0, sizeof(uint32_t), st);
-  if (e != cudaSuccess) return e;
-  grid_probe_kernel<<<(P.src.n + 255u) / 256u, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list);
+cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
+                             uint32_t capacity, cudaStream_t st) {
+  grid_table_init_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
+  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
+                              uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st) {
+  // *pending_count must be zero on entry: the previous probe (or the context) cleared it
+  const float cell = 1.0f / g.inv_cell;
+  const uint32_t grid = (P.src.n + 255u) / 256u;
+  if (blocks)
+    grid_probe_blocks_kernel<<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+  else
+    grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, next_count);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
-                                  uint32_t max_pending, int grid, cudaStream_t st) {
-  if (depth < 1) depth = 1;
-  const size_t smem = static_cast<size_t>(depth) * kLinBlock * (sizeof(uint2) + sizeof(float));
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(pending_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-  }
-  pending_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, depth, pending_count, pending_list, max_pending);
+                                  uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
+                                  cudaStream_t st) {
+  if (depth > kPendStack) return cudaErrorInvalidValue;
+  // block_table: the block-list table (enables the ring phase) or null
+  pending_search_kernel<<<grid, kLinBlock, 0, st>>>(P, pnodes, pending_count, pending_list, max_pending, grid_pts, block_table, capacity - 1u, g,
+                                                    1.0f / g.inv_cell);
   return cudaGetLastError();
 }
 

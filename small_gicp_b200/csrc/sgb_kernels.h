@@ -16,6 +16,7 @@ cudaError_t set_source_curve(int hilbert);
 int search_occupancy(int stack_depth);
 cudaError_t launch_search(const LinParams& P, int grid, int stack_depth, cudaStream_t st);
 cudaError_t launch_factor_reduce(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
+int factor_reduce_occupancy(int factor, int robust);
 
 cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bounds6, double* d_centre4, int sm_count, cudaStream_t st);
 cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,
@@ -43,12 +44,15 @@ struct __align__(16) GridSlot {
   uint32_t start, count;   // run of the cell's points in the cell-ordered copy of the target
 };
 cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* out, cudaStream_t st);
-cudaError_t launch_grid_build(const float4* leaf_pts, uint32_t n, const GridParams& g, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
-                              void* sort_temp, size_t sort_temp_bytes, float4* grid_pts, GridSlot* table, uint32_t capacity, cudaStream_t st);
-cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, uint8_t* state,
-                              uint32_t* pending_count, uint32_t* pending_list, cudaStream_t st);
+cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
+                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, cudaStream_t st);
+cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
+                             uint32_t capacity, cudaStream_t st);
+cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
+                              uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st);
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
-                                  uint32_t max_pending, int grid, cudaStream_t st);
+                                  uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
+                                  cudaStream_t st);
 // device-side tree construction (sgb_kernels.cu)
 constexpr uint32_t kLbvhLeafPoints = 32;
 cudaError_t launch_curve_keys(const float4* pts, size_t n, const double* centre4, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);

@@ -127,10 +127,37 @@ __global__ void __launch_bounds__(kLinBlock) nn_search_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Phase 2.
+// Phase 2.  One point per thread per tile of kLinBlock points.  The gather of the matched target point / covariance
+// depends on the correspondence index, and the FP64 factor algebra holds ~128 registers (4 CTAs / SM), so plain loads
+// left the kernel latency-bound (profiles/r01/k: 24 % issue slots, 1.4 TB/s).  The loads are therefore issued two
+// tiles ahead with cp.async into a per-thread landing zone in shared memory:
+//   A(t+2): correspondence index + source point / covariance (coalesced)
+//   B(t+1): target point / normal / covariance gathered through the index A(t+1) brought in
+//   C(t)  : FP64 rejector + factor algebra on the operands that landed during the previous tile's arithmetic
+// Every thread only reads what it copied itself, so the pipeline needs no barrier, just cp.async.wait_group.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int FACTOR>
+struct FactorFields {
+  // landing-zone slots (float4 each): source point [+ source covariance], target point [+ normal | covariance]
+  static constexpr int kSrc = FACTOR == 2 ? 3 : 1;
+  static constexpr int kAll = FACTOR == 2 ? 6 : (FACTOR == 1 ? 3 : 2);
+};
+constexpr int kFactorStages = 3;
+
 template <int FACTOR, int ROBUST>
-__global__ void __launch_bounds__(kLinBlock) factor_reduce_kernel(const __grid_constant__ LinParams P) {
+__global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ LinParams P) {
+  using F = FactorFields<FACTOR>;
+  extern __shared__ float4 s_zone[];  // [kFactorStages][F::kAll][kLinBlock]
+  __shared__ uint32_t s_corr[kFactorStages][kLinBlock];
   double acc[kAcc + 1];
 #pragma unroll
   for (int k = 0; k <= kAcc; k++) acc[k] = 0.0;
@@ -139,40 +166,114 @@ __global__ void __launch_bounds__(kLinBlock) factor_reduce_kernel(const __grid_c
   const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
   const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
   const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.src.n; i += stride) {
-    const uint32_t best = P.corr[i];
-    if (best == kNone) continue;
-    const float4 sp = __ldg(&P.src.pts[i]);
-    const double sx = sp.x, sy = sp.y, sz = sp.z;
-    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
-    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
-    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
-    const float4 tq = __ldg(&P.tgt.pts[best]);
-    const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
-    if (rx * rx + ry * ry + rz * rz > P.max_dist_sq_d) {  // DistanceRejector on the FP64 residual (rejector.hpp:24)
-      P.corr[i] = kNone;
-      continue;
-    }
-    Sym3 M;
-    if (FACTOR == 0) {
-      M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
-    } else if (FACTOR == 1) {
-      const float4 n = __ldg(&P.tgt.normals[best]);
-      M = Sym3{static_cast<double>(n.x) * n.x, 0.0, 0.0, static_cast<double>(n.y) * n.y, 0.0, static_cast<double>(n.z) * n.z};
+  const uint32_t n = P.src.n, n_tiles = (n + kLinBlock - 1u) / kLinBlock, tid = threadIdx.x;
+  float4* zone = s_zone + tid;
+  auto slot = [&](int stage, int f) { return zone + (stage * F::kAll + f) * kLinBlock; };
+  auto issue_a = [&](uint32_t tile, int stage) {
+    const uint32_t i = tile * kLinBlock + tid;
+    if (tile < n_tiles && i < n) {
+      cp_async4(&s_corr[stage][tid], &P.corr[i]);
+      cp_async16(slot(stage, 0), &P.src.pts[i]);
+      if (FACTOR == 2) {
+        cp_async16(slot(stage, 1), &P.src.covA[i]);
+        cp_async16(slot(stage, 2), &P.src.covB[i]);
+      }
     } else {
-      M = gicp_precision(R, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[best]), __ldg(&P.tgt.covB[best]));
+      s_corr[stage][tid] = kNone;
     }
-    accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
-    acc[kAcc] += 1.0;
+  };
+  auto issue_b = [&](int stage) {
+    const uint32_t best = s_corr[stage][tid];
+    if (best == kNone) return;
+    cp_async16(slot(stage, F::kSrc), &P.tgt.pts[best]);
+    if (FACTOR == 1) cp_async16(slot(stage, F::kSrc + 1), &P.tgt.normals[best]);
+    if (FACTOR == 2) {
+      cp_async16(slot(stage, F::kSrc + 1), &P.tgt.covA[best]);
+      cp_async16(slot(stage, F::kSrc + 2), &P.tgt.covB[best]);
+    }
+  };
+
+  const uint32_t G = gridDim.x;
+  uint32_t tile = blockIdx.x;
+  issue_a(tile, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  issue_b(0);
+  issue_a(tile + G, 1);
+  cp_async_commit();
+  int st = 0;
+  for (; tile < n_tiles; tile += G) {
+    cp_async_wait_all();  // B(tile) and A(tile + G) have landed
+    const int st1 = st == kFactorStages - 1 ? 0 : st + 1, st2 = st1 == kFactorStages - 1 ? 0 : st1 + 1;
+    issue_b(st1);
+    issue_a(tile + 2u * G, st2);
+    cp_async_commit();
+    const uint32_t best = s_corr[st][tid];
+    if (best != kNone) {
+      const uint32_t i = tile * kLinBlock + tid;
+      const float4 sp = *slot(st, 0);
+      const double sx = sp.x, sy = sp.y, sz = sp.z;
+      const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
+      const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
+      const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
+      const float4 tq = *slot(st, F::kSrc);
+      const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
+      if (rx * rx + ry * ry + rz * rz > P.max_dist_sq_d) {  // DistanceRejector on the FP64 residual (rejector.hpp:24)
+        P.corr[i] = kNone;
+      } else {
+        Sym3 M;
+        if (FACTOR == 0) {
+          M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+        } else if (FACTOR == 1) {
+          const float4 nrm = *slot(st, F::kSrc + 1);
+          M = Sym3{static_cast<double>(nrm.x) * nrm.x, 0.0, 0.0, static_cast<double>(nrm.y) * nrm.y, 0.0, static_cast<double>(nrm.z) * nrm.z};
+        } else {
+          M = gicp_precision(R, *slot(st, 1), *slot(st, 2), *slot(st, F::kSrc + 1), *slot(st, F::kSrc + 2));
+        }
+        accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
+        acc[kAcc] += 1.0;
+      }
+    }
+    st = st1;
   }
+  cp_async_wait_all();
   block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
 }
 
 template <int FACTOR, int ROBUST>
 static cudaError_t launch_factor(const LinParams& P, int grid, cudaStream_t st) {
-  factor_reduce_kernel<FACTOR, ROBUST><<<grid, kLinBlock, 0, st>>>(P);
+  const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
+  factor_reduce_kernel<FACTOR, ROBUST><<<grid, kLinBlock, smem, st>>>(P);
   return cudaGetLastError();
+}
+
+// resident CTAs per SM of one instantiation (the grid is sized to exactly one wave: a partial second wave of this
+// register-heavy kernel ran one CTA per SM for a third of the kernel's duration, profiles/r01/r)
+template <int FACTOR, int ROBUST>
+static int factor_ctas_per_sm() {
+  static int cached = 0;
+  if (cached) return cached;
+  const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
+  cudaFuncSetAttribute(factor_reduce_kernel<FACTOR, ROBUST>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<FACTOR, ROBUST>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+  cached = nb;
+  return nb;
+}
+
+int factor_reduce_occupancy(int factor, int robust) {
+  switch (factor * 3 + robust) {
+    case 0: return factor_ctas_per_sm<0, 0>();
+    case 1: return factor_ctas_per_sm<0, 1>();
+    case 2: return factor_ctas_per_sm<0, 2>();
+    case 3: return factor_ctas_per_sm<1, 0>();
+    case 4: return factor_ctas_per_sm<1, 1>();
+    case 5: return factor_ctas_per_sm<1, 2>();
+    case 6: return factor_ctas_per_sm<2, 0>();
+    case 7: return factor_ctas_per_sm<2, 1>();
+    case 8: return factor_ctas_per_sm<2, 2>();
+    default: return 1;
+  }
 }
 
 int search_occupancy(int stack_depth) {
