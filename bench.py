@@ -486,12 +486,12 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(n_src * 160 + 128),
                 "d2h_bytes_per_step": 44 * 8,
                 "ms_per_step": e2e_ms,
-                "what": "sgb_source_set_points (pinned host Vector4d+Matrix4d layout, device conversion + Morton sort) + sgb_linearize_device + D2H of H|b|e, per step",
+                "what": "sgb_source_set_points (pinned host Vector4d+Matrix4d layout, device conversion + Hilbert sort) + sgb_linearize_device + D2H of H|b|e, per step",
             },
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm",
-                "kernel": "sgb::packet_search_kernel + sgb::factor_reduce_kernel<2,0> (the two launches of one linearize)",
+                "kernel": "one sgb_linearize = sgb::grid_probe_blocks_kernel + pending_search_kernel | packet_search_kernel (picked on the device) + factor_reduce_kernel<2,0>: four launches, timed together",
                 "achieved": achieved,
                 "peak": peak,
                 "peak_source": peak_src,
@@ -500,6 +500,7 @@ def run_ours(args):
                 "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_ms_mean,
+                "launches_per_step": launches / max(1, args.steps),
             },
             "cpu_baseline": cpu_baseline,
             "value_l2_warm": total_points / (warm_ms * 1e-3) / 1e6,

@@ -23,12 +23,18 @@ echo "== bench (ours)"
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?" >> $OUT/bench.err
 tail -c 3500 $OUT/bench.json; tail -3 $OUT/bench.err
 
-echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+echo "== ncu launch list (setup: first 400 launches)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_setup.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
-echo "rc=$?"; wc -l $OUT/launches.csv
+echo "rc=$?"; wc -l $OUT/launches_setup.csv
 
-echo "== ncu full capture of the linearize kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"packet_search_kernel|factor_reduce_kernel" -s 16 -c 4 -f -o $OUT/prof_linearize \
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+KERNELS='regex:grid_probe|pending_search|packet_search|factor_reduce'
+echo "== ncu launch list of the timed region (the four launches of each linearize)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 40 -c 40 --csv --log-file $OUT/launches_timed.csv \
+    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches2.log 2>&1
+echo "rc=$?"; wc -l $OUT/launches_timed.csv
+
+echo "== ncu full capture of the linearize kernels (one pass over the 5 poses of the trajectory)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 40 -c 20 -f -o $OUT/prof_linearize \
+    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 echo "rc=$?"; ls -la $OUT | head -30

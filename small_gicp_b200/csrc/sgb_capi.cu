@@ -38,10 +38,11 @@ uint32_t host_vox_hash(int x, int y, int z) {  // must equal vox_hash() in sgb_d
 }
 
 int ensure_reduction_buffers(sgb_ctx* ctx, int grid) {
-  CU(ctx->partials.reserve(static_cast<size_t>(grid) * kPartialStride * sizeof(double)));
-  if (!ctx->ticket.p) {
-    CU(ctx->ticket.reserve(sizeof(unsigned int)));
-    CU(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  CU(ctx->partials.reserve(reduction_partials_doubles(static_cast<size_t>(grid)) * sizeof(double)));
+  const size_t ticket_bytes = reduction_tickets(static_cast<size_t>(grid)) * sizeof(unsigned int);
+  if (ticket_bytes > ctx->ticket.cap) {  // the kernels leave the counters zeroed; only a fresh buffer needs clearing
+    CU(ctx->ticket.reserve(ticket_bytes));
+    CU(cudaMemsetAsync(ctx->ticket.p, 0, ctx->ticket.cap, ctx->stream));
   }
   CU(ctx->out44.reserve(64 * sizeof(double)));
   return 0;
@@ -164,8 +165,7 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
       const uint8_t* settled = nullptr;
       const uint32_t* pending_count = nullptr;
       // more pending queries than this: packet search over the chunk-ordered queries, else a warp per pending query
-      static const int split_div = std::getenv("SGB_PENDING_DIV") ? std::max(1, std::atoi(std::getenv("SGB_PENDING_DIV"))) : 16;  // profiling switch
-      const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / split_div);
+      const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / static_cast<size_t>(ctx->pending_div));
       if (ctx->grid_ready) {
         // grid front end: settles every query whose nearest neighbour lies within half a cell (sgb_grid.cu)
         CU(ctx->grid_state.reserve(ctx->n_src));
@@ -186,16 +186,15 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
         CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->grid_state.as<uint8_t>(), pc,
                              plist, pbase + (ctx->pending_parity ^ 1), ctx->stream));
         ctx->pending_parity ^= 1;
-        static const bool ring = !(std::getenv("SGB_RING") && std::atoi(std::getenv("SGB_RING")) == 0);  // profiling switch
         CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, plist, pending_split, ctx->grid_pts.as<float4>(),
-                                 (ctx->grid_blocks && ring) ? ctx->grid_table.as<GridSlot>() : nullptr, ctx->grid_capacity, g, ctx->sm_count * 8, ctx->stream));
+                                 (ctx->grid_blocks && ctx->use_ring) ? ctx->grid_table.as<GridSlot>() : nullptr, ctx->grid_capacity, g, ctx->sm_count * 8,
+                                 ctx->stream));
         ctx->launches += 2;
         settled = ctx->grid_state.as<uint8_t>();
         pending_count = pc;
       }
       CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, ctx->stream));
-      static const bool debug_pending = std::getenv("SGB_DEBUG_PENDING") != nullptr;  // profiling aid: synchronises
-      if (debug_pending && pending_count) {
+      if (ctx->debug_pending && pending_count) {  // profiling aid: synchronises
         uint32_t h = 0;
         CU(cudaMemcpyAsync(&h, pending_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -212,6 +211,7 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
     if (fgrid > fcap) fgrid = fcap;
     if (int rc = ensure_reduction_buffers(ctx, fgrid)) return rc;
     P.partials = ctx->partials.as<double>();
+    P.ticket = ctx->ticket.as<unsigned int>();
     CU(launch_factor_reduce(P, factor, robust, fgrid, ctx->stream));
     ctx->launches += 2;
   } else {
@@ -298,6 +298,15 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
   if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
   if (const char* s = getenv("SGB_GRID")) ctx->use_grid = !(s[0] == '0');  // profiling switch: 0 = tree search only
+  // profiling switches of the grid front end (A/B runs in profiles/, variants exercised by tests/test_gpu_parity.py)
+  if (const char* s = getenv("SGB_GRID_BLOCKS")) ctx->grid_blocks_wanted = !(s[0] == '0');  // 0 = per-cell lists, eight lookups per query
+  if (const char* s = getenv("SGB_RING")) ctx->use_ring = !(s[0] == '0');                   // 0 = pending queries always walk the tree
+  if (const char* s = getenv("SGB_PENDING_DIV")) ctx->pending_div = std::max(1, atoi(s));   // packet search when more than n / div queries are pending
+  if (const char* s = getenv("SGB_GRID_CELL")) {                                            // cell edge in units of the median point spacing
+    const double v = atof(s);
+    if (v > 0.1 && v < 100.0) ctx->grid_cell_factor = v;
+  }
+  ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
     ctx->host_tree = (s[0] == 'h');
     if (s[0] == 'l') ctx->tree_quality = 0;

@@ -90,12 +90,7 @@ int build_grid(sgb_ctx* ctx) {
     if (sp[i] > 0.f) sp[k++] = sp[i];
   if (k == 0) return 0;
   std::nth_element(sp.begin(), sp.begin() + k / 2, sp.begin() + k);
-  double cell_factor = 3.0;  // cell edge in units of the median point spacing
-  if (const char* e = std::getenv("SGB_GRID_CELL")) {  // profiling switch
-    const double v = std::atof(e);
-    if (v > 0.1 && v < 100.0) cell_factor = v;
-  }
-  double cell = cell_factor * sp[k / 2];
+  double cell = ctx->grid_cell_factor * sp[k / 2];
   double ext = 0.0;
   for (int a = 0; a < 3; a++) ext = std::max(ext, bounds[3 + a] - bounds[a]);
   if (!(cell > 0.0) || !(ext > 0.0)) return 0;
@@ -105,8 +100,7 @@ int build_grid(sgb_ctx* ctx) {
   g.inv_cell = static_cast<float>(1.0 / cell);
   const double settle = (0.5 - 4e-3) * cell;  // margin for the FP32 cell-coordinate arithmetic (kGridSlack cells, sgb_grid.cu)
   g.settle_d2 = static_cast<float>(settle * settle);
-  static const bool blocks_env = !(std::getenv("SGB_GRID_BLOCKS") && std::atoi(std::getenv("SGB_GRID_BLOCKS")) == 0);  // profiling switch
-  const bool blocks = blocks_env;
+  const bool blocks = ctx->grid_blocks_wanted;
   const size_t n_ent = blocks ? n * 8 : n;  // block lists hold every point under its eight enclosing 2 x 2 x 2 blocks
   if (n_ent >= (1ull << 31)) return 0;
   CU(ctx->keys_in.reserve(n_ent * sizeof(uint64_t)));

@@ -238,10 +238,21 @@ __device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes,
   return best;
 }
 
-/// Block-wide sum of per-thread accumulators -> partials[blockIdx.x]; the last CTA to finish adds all
-/// partials in CTA order (deterministic) and writes the expanded 44-double result.
+/// CTAs per group of the two-level final reduction (see block_reduce_and_finish)
+constexpr unsigned int kFinishGroup = 16;
+/// doubles / tickets the reduction needs for a grid of `grid` CTAs
+__host__ __device__ inline size_t reduction_partials_doubles(size_t grid) { return (grid + (grid + kFinishGroup - 1) / kFinishGroup) * kPartialStride; }
+__host__ __device__ inline size_t reduction_tickets(size_t grid) { return 1 + (grid + kFinishGroup - 1) / kFinishGroup; }
+
+/// Block-wide sum of per-thread accumulators -> partials[blockIdx.x].  The sums of all CTAs are then combined by a
+/// two-level tree of tickets: the last CTA of every group of kFinishGroup consecutive CTAs adds that group's partials,
+/// the last group to finish adds the group sums and writes the (expanded 44-double) result.  Each level is one batch of
+/// independent L2 loads per lane -- a single CTA adding all gridDim.x partials cost ~15-25 us of an otherwise idle GPU
+/// (profiles/r01/p, r01/t).  The order of the additions depends on gridDim.x only: deterministic.
+/// partials: reduction_partials_doubles(gridDim.x) doubles; ticket: reduction_tickets(gridDim.x) zeroed counters (left zeroed).
 template <int NACC, bool EXPAND>
 __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out) {
+  static_assert(NACC <= 32, "one lane per accumulator");
   __shared__ double s_red[kLinBlock / 32][NACC];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -261,31 +272,39 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
   }
   __threadfence();
   __syncthreads();
+  const unsigned int group = blockIdx.x / kFinishGroup, n_groups = (gridDim.x + kFinishGroup - 1) / kFinishGroup;
+  const unsigned int group_first = group * kFinishGroup;
+  const unsigned int group_size = min(kFinishGroup, gridDim.x - group_first);
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+    const unsigned int t = atomicAdd(&ticket[1 + group], 1u);
+    s_last = (t == group_size - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // The whole CTA adds the partials (a single thread per sum chasing gridDim.x L2 round trips left every other SM idle
-  // for ~25 us, profiles/r01/p): warp g sums CTAs g, g + W, g + 2W, ... with several loads in flight, then the W
-  // group sums are added in group order.  The order is fixed by (gridDim.x, W) alone, so the result is deterministic.
-  {
-    constexpr int W = kLinBlock / 32;
-    static_assert(NACC <= 32, "one lane per accumulator");
-    double v = 0.0;
-    if (lane < NACC) {
-#pragma unroll 8
-      for (unsigned int b = warp; b < gridDim.x; b += W) v += __ldcg(&partials[static_cast<size_t>(b) * kPartialStride + lane]);
-      s_red[warp][lane] = v;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
+  double* group_sums = partials + static_cast<size_t>(gridDim.x) * kPartialStride;
+  if (threadIdx.x < NACC) {  // level 1: this group's CTAs, in CTA order
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kLinBlock / 32; w++) v += s_red[w][threadIdx.x];
+    for (unsigned int j = 0; j < kFinishGroup; j++)
+      if (j < group_size) v += __ldcg(&partials[static_cast<size_t>(group_first + j) * kPartialStride + threadIdx.x]);
+    group_sums[static_cast<size_t>(group) * kPartialStride + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ticket[1 + group] = 0u;  // ready for the next launch on this stream
+    const unsigned int t = atomicAdd(&ticket[0], 1u);
+    s_last = (t == n_groups - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) ticket[0] = 0u;
+  if (threadIdx.x < NACC) {  // level 2: the group sums, in group order
+    double v = 0.0;
+#pragma unroll 8
+    for (unsigned int gI = 0; gI < n_groups; gI++) v += __ldcg(&group_sums[static_cast<size_t>(gI) * kPartialStride + threadIdx.x]);
     if (!EXPAND) {
       out[threadIdx.x] = v;
     } else {
@@ -315,7 +334,6 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
       }
     }
   }
-  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
 }
 
 }  // namespace sgb

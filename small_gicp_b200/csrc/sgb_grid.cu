@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
                                                                uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,7 +490,15 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
   const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
   if (blocks)
-    grid_probe_blocks_kernel<<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+  {
+    static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;  // profiling switch
+    if (ctas == 6)
+      grid_probe_blocks_kernel<6><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    else if (ctas == 8)
+      grid_probe_blocks_kernel<8><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    else
+      grid_probe_blocks_kernel<5><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+  }
   else
     grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, next_count);
   return cudaGetLastError();

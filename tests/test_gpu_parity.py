@@ -290,19 +290,31 @@ def test_synthetic_200k_gicp(synthetic_pair):
 
 
 def test_search_structures_agree(synthetic_pair, monkeypatch):
-    """Exact NN is independent of the search structure: device-built linear BVH (default), host-built median-split
-    kd-tree, adopted reference kd-tree; packet, per-thread and fused kernels -- same correspondences, same sums."""
+    """Exact NN is independent of the search structure: device-built kd-tree (default), host-built median-split
+    kd-tree, adopted reference kd-tree; grid front end with block lists / per-cell lists / off, ring search on / off,
+    every pending query through the warp-per-query kernel or through the packet search, cells so small that most
+    queries stay pending; packet, per-thread and fused kernels -- same correspondences, same sums."""
     tc, tt, sc, Tgt, nt = synthetic_pair
     sg = _sg()
     results = {}
+    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL")
     for name, env, own in (
-        ("device-lbvh/packet", {}, True),
+        ("device-kd/grid", {}, True),
+        ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
+        ("device-kd/grid-cells", {"SGB_GRID_BLOCKS": "0"}, True),
+        ("device-kd/grid-no-ring", {"SGB_RING": "0"}, True),
+        ("device-kd/grid-warp-per-pending", {"SGB_PENDING_DIV": "1"}, True),
+        ("device-kd/grid-packet-pending", {"SGB_PENDING_DIV": "1000000"}, True),
+        ("device-kd/grid-small-cells", {"SGB_GRID_CELL": "0.7"}, True),
+        ("device-kd/grid-small-cells-warp", {"SGB_GRID_CELL": "0.7", "SGB_PENDING_DIV": "1"}, True),
+        ("device-kd/grid-large-cells", {"SGB_GRID_CELL": "6"}, True),
+        ("device-lbvh/grid", {"SGB_TREE": "lbvh"}, True),
         ("host-kd/packet", {"SGB_TREE": "host"}, True),
         ("reference-kd/packet", {}, False),
         ("reference-kd/per-thread", {"SGB_SEARCH": "1"}, False),
         ("host-kd/fused", {"SGB_SEARCH": "0"}, True),
     ):
-        for k in ("SGB_TREE", "SGB_SEARCH"):
+        for k in switches:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -315,6 +327,43 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     for name, (H, b, e, c) in results.items():
         assert (c != c0).sum() <= 3, name
         assert np.linalg.norm(H - H0) <= 1e-6 * np.linalg.norm(H0) and abs(e - e0) <= 1e-6 * e0, name
+
+
+def test_grid_far_and_unbounded_queries(synthetic_pair, monkeypatch):
+    """Queries the grid front end cannot settle: a source displaced by metres (nothing within the 2.5-cell ring), no
+    rejector at all (unbounded search radius -> tree fallback), a tiny and a huge correspondence distance.  The grid
+    path must return what the pure tree search returns."""
+    tc, tt, sc, Tgt, nt = synthetic_pair
+    sg = _sg()
+    far = Tgt.copy()
+    far[:3, 3] += np.array([2.5, -1.5, 0.7])
+    cases = (
+        (Tgt, sg.REJECT_NONE, 0.0),
+        (far, sg.REJECT_NONE, 0.0),
+        (far, sg.REJECT_DISTANCE, 1.0),
+        (far, sg.REJECT_DISTANCE, 25.0),
+        (Tgt, sg.REJECT_DISTANCE, 1e-3),
+        (Tgt, sg.REJECT_DISTANCE, 400.0),
+    )
+    out = {}
+    for name, env in (("grid", {}), ("tree", {"SGB_GRID": "0"}), ("grid-warp", {"SGB_PENDING_DIV": "1"})):
+        for k in ("SGB_GRID", "SGB_PENDING_DIV"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = load_ctx(tc, tt, sc, own_tree=True)
+        res = []
+        for T, rej, md in cases:
+            H, b, e = ctx.linearize(T, factor=sg.FACTOR_GICP, rejector=rej, max_dist_sq=md)
+            res.append((H, e, ctx.correspondences(), ctx.num_inliers()))
+        out[name] = res
+        ctx.close()
+    for name in ("grid", "grid-warp"):
+        for k, ((H, e, c, ni), (H0, e0, c0, ni0)) in enumerate(zip(out[name], out["tree"])):
+            assert (c != c0).sum() <= 3, (name, k, int((c != c0).sum()))
+            assert abs(ni - ni0) <= 3, (name, k)
+            assert np.linalg.norm(H - H0) <= 1e-6 * max(np.linalg.norm(H0), 1e-30) and abs(e - e0) <= 1e-6 * max(e0, 1e-30), (name, k)
+    assert out["tree"][1][3] == len(sc)  # no rejector: every source point keeps a correspondence, however far
 
 
 def test_full_size_properties():
