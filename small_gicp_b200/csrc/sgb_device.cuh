@@ -180,6 +180,94 @@ __device__ __forceinline__ void accumulate_factor(const double* R, const Sym3& M
   acc[27] += w * e;
 }
 
+/// GICP weight in the SOURCE frame.  With R orthogonal,  R^T (Ct + R Cs R^T)^-1 R = (R^T Ct R + Cs)^-1 =: D.  D is all the
+/// Hessian blocks need (H_tt = D, H_rt = skew(p) D, H_rr = skew(p)^T D skew(p)), and  R^T M r = D (R^T r),
+/// r^T M r = (R^T r)^T D (R^T r):  the target-frame precision matrix M of gicp_factor.hpp:59-60 never has to be formed
+/// (~50 of the ~240 FP64 operations per point of the target-frame formulation above; same value up to rounding).
+__device__ __forceinline__ Sym3 gicp_precision_source(const double* R, const float4& sA, const float4& sB, const float4& tA, const float4& tB) {
+  const double txx = tA.x, txy = tA.y, txz = tA.z, tyy = tA.w, tyz = tB.x, tzz = tB.y;
+  double B[9];  // B = Ct * R
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double r0 = R[0 + j], r1 = R[3 + j], r2 = R[6 + j];
+    B[0 + j] = txx * r0 + txy * r1 + txz * r2;
+    B[3 + j] = txy * r0 + tyy * r1 + tyz * r2;
+    B[6 + j] = txz * r0 + tyz * r1 + tzz * r2;
+  }
+  Sym3 n;  // N = Cs + R^T B
+  n.xx = static_cast<double>(sA.x) + (R[0] * B[0] + R[3] * B[3] + R[6] * B[6]);
+  n.xy = static_cast<double>(sA.y) + (R[0] * B[1] + R[3] * B[4] + R[6] * B[7]);
+  n.xz = static_cast<double>(sA.z) + (R[0] * B[2] + R[3] * B[5] + R[6] * B[8]);
+  n.yy = static_cast<double>(sA.w) + (R[1] * B[1] + R[4] * B[4] + R[7] * B[7]);
+  n.yz = static_cast<double>(sB.x) + (R[1] * B[2] + R[4] * B[5] + R[7] * B[8]);
+  n.zz = static_cast<double>(sB.y) + (R[2] * B[2] + R[5] * B[5] + R[8] * B[8]);
+  return sym3_inverse(n);
+}
+
+/// Point-to-plane weight diag(n.^2) (plane_icp_factor.hpp:46-55) carried to the source frame: D = R^T diag(n.^2) R.
+__device__ __forceinline__ Sym3 plane_weight_source(const double* R, double nx, double ny, double nz) {
+  const double a = nx * nx, b = ny * ny, c = nz * nz;
+  Sym3 d;
+  d.xx = a * R[0] * R[0] + b * R[3] * R[3] + c * R[6] * R[6];
+  d.xy = a * R[0] * R[1] + b * R[3] * R[4] + c * R[6] * R[7];
+  d.xz = a * R[0] * R[2] + b * R[3] * R[5] + c * R[6] * R[8];
+  d.yy = a * R[1] * R[1] + b * R[4] * R[4] + c * R[7] * R[7];
+  d.yz = a * R[1] * R[2] + b * R[4] * R[5] + c * R[7] * R[8];
+  d.zz = a * R[2] * R[2] + b * R[5] * R[5] + c * R[8] * R[8];
+  return d;
+}
+
+/// Same sums as accumulate_factor, from the source-frame weight D = R^T M R and the source-frame residual rs = R^T r.
+template <int ROBUST>
+__device__ __forceinline__ void accumulate_factor_source(const Sym3& D, double rsx, double rsy, double rsz, double px, double py, double pz, double robust_c,
+                                                         double* acc) {
+  const double mrx = D.xx * rsx + D.xy * rsy + D.xz * rsz;
+  const double mry = D.xy * rsx + D.yy * rsy + D.yz * rsz;
+  const double mrz = D.xz * rsx + D.yz * rsy + D.zz * rsz;
+  const double e = 0.5 * (rsx * mrx + rsy * mry + rsz * mrz);
+  double w = 1.0;
+  if (ROBUST == 1) {  // Huber, robust_kernel.hpp:24-27 on sqrt(e) (robust_kernel.hpp:84)
+    const double x = sqrt(e);
+    w = x < robust_c ? 1.0 : robust_c / x;
+  } else if (ROBUST == 2) {  // Cauchy, robust_kernel.hpp:47 : c / (c + x^2) with x = sqrt(e)
+    const double x = sqrt(e);
+    w = robust_c / (robust_c + x * x);
+  }
+  const double d00 = w * D.xx, d01 = w * D.xy, d02 = w * D.xz, d11 = w * D.yy, d12 = w * D.yz, d22 = w * D.zz;
+  const double gx = w * mrx, gy = w * mry, gz = w * mrz;  // g = w R^T M r
+  const double u00 = py * d02 - pz * d01, u01 = py * d12 - pz * d11, u02 = py * d22 - pz * d12;
+  const double u10 = pz * d00 - px * d02, u11 = pz * d01 - px * d12, u12 = pz * d02 - px * d22;
+  const double u20 = px * d01 - py * d00, u21 = px * d11 - py * d01, u22 = px * d12 - py * d02;
+  acc[0] += py * u02 - pz * u01;
+  acc[1] += pz * u00 - px * u02;
+  acc[2] += px * u01 - py * u00;
+  acc[3] += pz * u10 - px * u12;
+  acc[4] += px * u11 - py * u10;
+  acc[5] += px * u21 - py * u20;
+  acc[6] += u00;
+  acc[7] += u01;
+  acc[8] += u02;
+  acc[9] += u10;
+  acc[10] += u11;
+  acc[11] += u12;
+  acc[12] += u20;
+  acc[13] += u21;
+  acc[14] += u22;
+  acc[15] += d00;
+  acc[16] += d01;
+  acc[17] += d02;
+  acc[18] += d11;
+  acc[19] += d12;
+  acc[20] += d22;
+  acc[21] += gy * pz - gz * py;
+  acc[22] += gz * px - gx * pz;
+  acc[23] += gx * py - gy * px;
+  acc[24] -= gx;
+  acc[25] -= gy;
+  acc[26] -= gz;
+  acc[27] += w * e;
+}
+
 /// Exact nearest neighbour of q in the flattened kd-tree (restates the visiting order of
 /// UnsafeKdTree::knn_search, ann/kdtree.hpp:193-233, with an explicit stack of far children).
 /// `best_d` enters as the search bound (only strictly closer points are accepted, knn_result.hpp:81-83).

@@ -221,16 +221,18 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
       if (rx * rx + ry * ry + rz * rz > P.max_dist_sq_d) {  // DistanceRejector on the FP64 residual (rejector.hpp:24)
         P.corr[i] = kNone;
       } else {
-        Sym3 M;
+        // weight and residual in the SOURCE frame (D = R^T M R, rs = R^T r): see gicp_precision_source
+        Sym3 D;
         if (FACTOR == 0) {
-          M = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+          D = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
         } else if (FACTOR == 1) {
           const float4 nrm = *slot(st, F::kSrc + 1);
-          M = Sym3{static_cast<double>(nrm.x) * nrm.x, 0.0, 0.0, static_cast<double>(nrm.y) * nrm.y, 0.0, static_cast<double>(nrm.z) * nrm.z};
+          D = plane_weight_source(R, nrm.x, nrm.y, nrm.z);
         } else {
-          M = gicp_precision(R, *slot(st, 1), *slot(st, 2), *slot(st, F::kSrc + 1), *slot(st, F::kSrc + 2));
+          D = gicp_precision_source(R, *slot(st, 1), *slot(st, 2), *slot(st, F::kSrc + 1), *slot(st, F::kSrc + 2));
         }
-        accumulate_factor<ROBUST>(R, M, rx, ry, rz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
+        const double rsx = R[0] * rx + R[3] * ry + R[6] * rz, rsy = R[1] * rx + R[4] * ry + R[7] * rz, rsz = R[2] * rx + R[5] * ry + R[8] * rz;
+        accumulate_factor_source<ROBUST>(D, rsx, rsy, rsz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
         acc[kAcc] += 1.0;
       }
     }
