@@ -293,7 +293,7 @@ def workload_config(args, inp):
         "points_source_per_gpu": args.points,
         "covariances": inp["covs"],
         "l2": "flushed between timed steps (256 MiB write)",
-        "parallelism": f"source sharded over {args.gpus} GPU(s), target + kd-tree replicated, NCCL all-reduce of H|b|e (44 doubles) per step" if args.gpus > 1 else "single GPU",
+        "parallelism": f"source sharded over {args.gpus} GPU(s), target + kd-tree replicated, all-reduce of H|b|e (44 doubles) per step (see allreduce)" if args.gpus > 1 else "single GPU",
     }
 
 
@@ -327,6 +327,14 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
+    # N > 1: the all-reduce of H|b|e is fused into the reduction kernel (peer mailboxes over NVLink); SGB_FUSED_ALLREDUCE=0
+    # selects the NCCL all_reduce of the 44 doubles instead (A/B)
+    fused = False
+    if use_dist and os.environ.get("SGB_FUSED_ALLREDUCE", "1") != "0":
+        from small_gicp_b200.distributed import connect_fused
+
+        fused = connect_fused(ctx)
+    nccl = use_dist and not fused
     ctx.set_target(inp["target"], None, inp["target_covs"])
     ctx.build_target_kdtree(args.leaf)
     # pinned host copies of the step's inputs for the e2e leg
@@ -338,7 +346,7 @@ def run_ours(args):
 
     def step_device(T):
         ctx.linearize_device(T, out.data_ptr(), factor=sg.FACTOR_GICP, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0)
-        if use_dist:
+        if nccl:
             dist.all_reduce(out[:44])
 
     def linearize_host(T):
@@ -375,7 +383,7 @@ def run_ours(args):
         kev[i][0].record(stream)
         ctx.linearize_device(T, out.data_ptr(), factor=sg.FACTOR_GICP, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0)
         kev[i][1].record(stream)
-        if use_dist:
+        if nccl:
             dist.all_reduce(out[:44])
         ev[i][1].record(stream)
     barrier()
@@ -478,7 +486,7 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f32 search / f64 factor algebra + sums",
             "data": "synthetic",
-            "config": workload_config(args, inp),
+            "config": dict(workload_config(args, inp), allreduce=("none (single GPU)" if not use_dist else "fused into factor_reduce_kernel: peer mailboxes over NVLink (sgb_comm_*)" if fused else "NCCL all_reduce of 44 doubles after the kernel")),
             "clocks": clocks,
             "e2e": {
                 "value": total_points / (e2e_ms * 1e-3) / 1e6,
@@ -507,6 +515,8 @@ def run_ours(args):
             "pose_error_vs_gt": {"rot_rad": rot_err, "trans_m": trans_err, "gn_iterations": len(poses)},
         }
         print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()  # nobody unmaps a mailbox a peer may still write to
     ctx.close()
     if use_dist:
         dist.destroy_process_group()

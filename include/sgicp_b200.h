@@ -57,6 +57,22 @@ int sgb_synchronize(sgb_ctx* ctx);
 /* Number of this library's kernels launched by the context since creation (bench.py gpu_launches). */
 uint64_t sgb_kernel_launches(const sgb_ctx* ctx);
 
+/* ---- multi-GPU (one process per GPU, source sharded, target replicated).  The reference has no
+ *      counterpart: its reductions (reduction_omp.hpp:24-58, reduction_tbb.hpp:70-92) sum within one process.  After
+ *      sgb_comm_connect* every sgb_linearize* / sgb_error* of this context returns the SUM OVER ALL RANKS: the CTA that
+ *      finishes the reduction writes its sums straight into the peers' mailboxes over NVLink and adds theirs (one kernel,
+ *      no NCCL call, deterministic rank order).  All ranks must issue the same sequence of linearize / error calls. ---- */
+#define SGB_COMM_HANDLE_BYTES 64
+#define SGB_COMM_MAX_RANKS 8
+/* CUDA IPC handle (64 bytes) of this context's mailbox; allocate it on first use. */
+int sgb_comm_handle(sgb_ctx* ctx, void* out_handle64);
+/* `handles` = world x 64 bytes, rank order, gathered by the caller (e.g. torch.distributed.all_gather). */
+int sgb_comm_connect(sgb_ctx* ctx, int rank, int world, const void* handles);
+/* Same wiring from raw device pointers (contexts of ONE process: tests, single-process multi-stream setups). */
+int sgb_comm_mailbox(sgb_ctx* ctx, void** out_device_ptr);
+int sgb_comm_connect_ptrs(sgb_ctx* ctx, int rank, int world, void* const* mailboxes);
+int sgb_comm_disconnect(sgb_ctx* ctx);
+
 /* ---- target: replaces traits::point/normal/cov(target, k) (points/traits.hpp:38-54) and the
  *      target_tree argument of Reduction::linearize (reduction.hpp:23) -------------------------- */
 int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points_xyz1, const double* normals_xyz0 /*or NULL*/,

@@ -26,6 +26,11 @@ _SIGNATURES = {
     "sgb_set_stream": (C.c_int, [_vp, _vp]),
     "sgb_synchronize": (C.c_int, [_vp]),
     "sgb_kernel_launches": (C.c_uint64, [_vp]),
+    "sgb_comm_handle": (C.c_int, [_vp, _vp]),
+    "sgb_comm_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "sgb_comm_mailbox": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "sgb_comm_connect_ptrs": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "sgb_comm_disconnect": (C.c_int, [_vp]),
     "sgb_target_set_points": (C.c_int, [_vp, C.c_size_t, _dp, _dp, _dp]),
     "sgb_target_set_kdtree": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _u64p]),
     "sgb_target_build_kdtree": (C.c_int, [_vp, C.c_int]),
@@ -207,6 +212,35 @@ class Context:
         out = np.empty(self.source_size, dtype=np.uint64)
         self._check(self._L.sgb_correspondences(self._h, out.ctypes.data_as(_u64p)))
         return out
+
+    # ---- multi-GPU: all-reduce of H|b|e fused into the reduction kernel (peer memory over NVLink) ----
+    COMM_HANDLE_BYTES = 64
+
+    def comm_handle(self):
+        """64-byte CUDA IPC handle of this context's mailbox (to be all-gathered across the ranks)"""
+        buf = (C.c_ubyte * self.COMM_HANDLE_BYTES)()
+        self._check(self._L.sgb_comm_handle(self._h, C.cast(buf, _vp)))
+        return bytes(buf)
+
+    def comm_connect(self, rank, world, handles):
+        """handles: world x 64 bytes in rank order; afterwards linearize()/error() return the sum over all ranks"""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        assert len(blob) == world * self.COMM_HANDLE_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._L.sgb_comm_connect(self._h, int(rank), int(world), C.cast(buf, _vp)))
+
+    def comm_mailbox(self):
+        """device address of this context's mailbox (wiring contexts of one process: tests)"""
+        p = _vp()
+        self._check(self._L.sgb_comm_mailbox(self._h, C.byref(p)))
+        return int(p.value)
+
+    def comm_connect_ptrs(self, rank, world, mailboxes):
+        arr = (_vp * world)(*[_vp(int(m)) for m in mailboxes])
+        self._check(self._L.sgb_comm_connect_ptrs(self._h, int(rank), int(world), arr))
+
+    def comm_disconnect(self):
+        self._check(self._L.sgb_comm_disconnect(self._h))
 
     def num_inliers(self):
         n = C.c_size_t(0)

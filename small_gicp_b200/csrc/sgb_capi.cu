@@ -106,6 +106,12 @@ int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
   P.corr = ctx->corr.as<uint32_t>();
   P.partials = ctx->partials.as<double>();
   P.ticket = ctx->ticket.as<unsigned int>();
+  if (ctx->comm_world > 1) {  // the launch that finishes the reduction also exchanges it with the other ranks
+    P.comm.world = ctx->comm_world;
+    P.comm.rank = ctx->comm_rank;
+    for (int p = 0; p < ctx->comm_world; p++) P.comm.mail[p] = ctx->comm_peers[p];
+    P.comm.seq = ++ctx->comm_seq;  // exactly one reduction per fill_params (do_linearize / do_error)
+  }
   return 0;
 }
 
@@ -115,7 +121,16 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
   CU(cudaSetDevice(ctx->device));
   ctx->last_out = d_out;
   if (ctx->n_src == 0 || ctx->n_tgt == 0) {  // empty clouds must not crash (helper_test.cpp:53-59): sum over nothing
-    CU(cudaMemsetAsync(d_out, 0, 44 * sizeof(double), ctx->stream));
+    if (ctx->comm_world > 1) {  // an empty shard still takes part in the exchange: contribute zeros
+      if (int rc = ensure_reduction_buffers(ctx, 1)) return rc;
+      LinParams P0;
+      fill_params(ctx, P0, T);
+      P0.out = d_out;
+      CU(launch_reduce_nothing(P0, true, ctx->stream));
+      ctx->launches += 1;
+    } else {
+      CU(cudaMemsetAsync(d_out, 0, 44 * sizeof(double), ctx->stream));
+    }
     if (ctx->n_src) {
       CU(ctx->corr.reserve(ctx->n_src * sizeof(uint32_t)));
       CU(cudaMemsetAsync(ctx->corr.p, 0xFF, ctx->n_src * sizeof(uint32_t), ctx->stream));
@@ -136,7 +151,9 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
   int grid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
   const int cap = ctx->sm_count * occ;
   if (grid > cap) grid = cap;
-  if (int rc = ensure_reduction_buffers(ctx, grid)) return rc;
+  // one allocation that serves every kernel that may finish the reduction (growing a buffer later would cudaFree, i.e.
+  // synchronise the whole device in the middle of the call)
+  if (int rc = ensure_reduction_buffers(ctx, std::max(grid, ctx->sm_count * 8))) return rc;
   CU(ctx->corr.reserve(ctx->n_src * sizeof(uint32_t)));
 
   LinParams P;
@@ -233,7 +250,16 @@ int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
   if (!ctx->have_lin) return fail(ctx, 1, "sgb_error: no preceding sgb_linearize (the correspondences are cached there)");
   CU(cudaSetDevice(ctx->device));
   if (ctx->n_src == 0 || ctx->n_tgt == 0) {
-    CU(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
+    if (ctx->comm_world > 1) {
+      if (int rc = ensure_reduction_buffers(ctx, 1)) return rc;
+      LinParams P0;
+      fill_params(ctx, P0, T);
+      P0.out = d_out;
+      CU(launch_reduce_nothing(P0, false, ctx->stream));
+      ctx->launches += 1;
+    } else {
+      CU(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
+    }
     return 0;
   }
   int grid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
@@ -327,6 +353,8 @@ void sgb_destroy(sgb_ctx* ctx) {
                     &ctx->pre_boxes, &ctx->grid_pending, &ctx->grid_pts, &ctx->grid_table, &ctx->grid_state, &ctx->grid_spacing, &ctx->pre_pts, &ctx->pre_leaf_pts, &ctx->pre_nodes, &ctx->pre_perm, &ctx->pre_centre, &ctx->pre_bounds, &ctx->pre_out_normals, &ctx->pre_out_covs, &ctx->pre_heads, &ctx->pre_slots, &ctx->pre_vals_out,
                     &ctx->sort_temp,    &ctx->corr,             &ctx->partials,      &ctx->ticket,        &ctx->out44,    &ctx->corr64};
   for (DevBuf* b : bufs) b->release();
+  sgb_comm_disconnect(ctx);
+  ctx->comm_mail.release();
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -350,6 +378,93 @@ int sgb_synchronize(sgb_ctx* ctx) {
 }
 
 uint64_t sgb_kernel_launches(const sgb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- multi-GPU exchange ----------------------------------------------------------------------
+static int comm_ensure_mailbox(sgb_ctx* ctx) {
+  if (ctx->comm_mail.p) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->comm_mail.reserve(kMailBytes));
+  CU(cudaMemset(ctx->comm_mail.p, 0, ctx->comm_mail.cap));  // flags = 0: no call has sequence number 0
+  return 0;
+}
+
+int sgb_comm_mailbox(sgb_ctx* ctx, void** out_device_ptr) {
+  if (!ctx || !out_device_ptr) return 1;
+  if (int rc = comm_ensure_mailbox(ctx)) return rc;
+  *out_device_ptr = ctx->comm_mail.p;
+  return 0;
+}
+
+int sgb_comm_handle(sgb_ctx* ctx, void* out_handle64) {
+  if (!ctx || !out_handle64) return 1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == SGB_COMM_HANDLE_BYTES, "IPC handle size");
+  if (int rc = comm_ensure_mailbox(ctx)) return rc;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->comm_mail.p));
+  std::memcpy(out_handle64, &h, sizeof(h));
+  return 0;
+}
+
+int sgb_comm_disconnect(sgb_ctx* ctx) {
+  if (!ctx) return 1;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int p = 0; p < kMaxPeers; p++) {
+    if (ctx->comm_ipc_opened[p] && ctx->comm_peers[p]) cudaIpcCloseMemHandle(ctx->comm_peers[p]);
+    ctx->comm_ipc_opened[p] = false;
+    ctx->comm_peers[p] = nullptr;
+  }
+  ctx->comm_world = 0;
+  ctx->comm_rank = 0;
+  return 0;
+}
+
+int sgb_comm_connect_ptrs(sgb_ctx* ctx, int rank, int world, void* const* mailboxes) {
+  if (!ctx) return 1;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !mailboxes) return fail(ctx, 1, "sgb_comm_connect: need 1 <= world <= 8, 0 <= rank < world");
+  if (int rc = comm_ensure_mailbox(ctx)) return rc;
+  sgb_comm_disconnect(ctx);
+  for (int p = 0; p < world; p++) {
+    if (!mailboxes[p]) return fail(ctx, 1, "sgb_comm_connect: null mailbox");
+    ctx->comm_peers[p] = static_cast<unsigned char*>(mailboxes[p]);
+  }
+  if (ctx->comm_peers[rank] != ctx->comm_mail.p) return fail(ctx, 1, "sgb_comm_connect: mailboxes[rank] is not this context's mailbox");
+  // a fresh epoch: clear the flags and restart the sequence (every rank does the same before its first exchange;
+  // the caller separates connect from the first linearize by a barrier, as with any communicator construction)
+  CU(cudaMemset(ctx->comm_mail.p, 0, ctx->comm_mail.cap));
+  ctx->comm_seq = 0;
+  ctx->comm_world = world;
+  ctx->comm_rank = rank;
+  return 0;
+}
+
+int sgb_comm_connect(sgb_ctx* ctx, int rank, int world, const void* handles) {
+  if (!ctx) return 1;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !handles) return fail(ctx, 1, "sgb_comm_connect: need 1 <= world <= 8, 0 <= rank < world");
+  if (int rc = comm_ensure_mailbox(ctx)) return rc;
+  sgb_comm_disconnect(ctx);
+  CU(cudaSetDevice(ctx->device));
+  void* ptrs[kMaxPeers] = {};
+  bool opened[kMaxPeers] = {};
+  for (int p = 0; p < world; p++) {
+    if (p == rank) {
+      ptrs[p] = ctx->comm_mail.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const unsigned char*>(handles) + static_cast<size_t>(p) * SGB_COMM_HANDLE_BYTES, sizeof(h));
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptrs[p], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < p; q++)
+        if (opened[q]) cudaIpcCloseMemHandle(ptrs[q]);
+      return fail(ctx, 2, std::string("sgb_comm_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+    }
+    opened[p] = true;
+  }
+  if (int rc = sgb_comm_connect_ptrs(ctx, rank, world, ptrs)) return rc;
+  for (int p = 0; p < world; p++) ctx->comm_ipc_opened[p] = opened[p];
+  return 0;
+}
 size_t sgb_target_size(const sgb_ctx* ctx) { return ctx ? ctx->n_tgt : 0; }
 size_t sgb_source_size(const sgb_ctx* ctx) { return ctx ? ctx->n_src : 0; }
 
@@ -538,6 +653,16 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   }
   CU(ctx->tmp_pts.reserve(n * sizeof(float4)));
   CU(ctx->src_pts.reserve(n * sizeof(float4)));
+  // per-query scratch of linearize, sized here so that linearize itself never (re)allocates -- a cudaFree there would
+  // synchronise the device in the middle of an asynchronous call
+  CU(ctx->corr.reserve(n * sizeof(uint32_t)));
+  CU(ctx->grid_state.reserve(n));
+  {
+    const void* before = ctx->grid_pending.p;
+    CU(ctx->grid_pending.reserve((n + 2) * sizeof(uint32_t)));
+    if (ctx->grid_pending.p != before) ctx->pending_clean = false;
+  }
+  if (int rc = ensure_reduction_buffers(ctx, ctx->sm_count * 8)) return rc;
   CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
   CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
   CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));

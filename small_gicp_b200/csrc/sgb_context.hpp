@@ -88,6 +88,13 @@ struct sgb_ctx {
   // ---- preprocessing scratch (sgb_capi_preprocess.cu) ----
   sgb::DevBuf pre_pts, pre_leaf_pts, pre_nodes, pre_perm, pre_centre, pre_bounds, pre_out_normals, pre_out_covs, pre_heads, pre_slots, pre_vals_out;
 
+  // ---- multi-GPU exchange fused into the reduction's finishing CTA (sgb_comm_*, CommParams in sgb_device.cuh) ----
+  sgb::DevBuf comm_mail;                  // this rank's mailbox (zeroed at allocation)
+  unsigned char* comm_peers[8] = {};      // mailbox of every rank as mapped into this process (own entry = comm_mail.p)
+  bool comm_ipc_opened[8] = {};           // mapped by cudaIpcOpenMemHandle (to be closed)
+  int comm_world = 0, comm_rank = 0;      // world <= 1: single GPU
+  unsigned long long comm_seq = 0;        // collective calls issued so far
+
   // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
   bool have_lin = false;
   bool corr_seeds = false;  // corr[] holds correspondences of the current (target, tree, source) triple

@@ -40,9 +40,26 @@ struct DevSource {
                  // i.e. one lane walks K spatially consecutive points while every load of the warp stays coalesced
 };
 
+/// Multi-GPU exchange fused into the finishing CTA of the reduction (one process per GPU, source sharded).
+/// Every rank owns a MAILBOX in its device memory that its peers map through CUDA IPC:
+///   doubles [2 parities][kMaxPeers senders][kMailStride]   then   unsigned long long flags [2 parities][kMaxPeers senders]
+/// Rank r stores its sums into slot (parity, r) of every peer's mailbox over NVLink, fences, stores the call's sequence
+/// number into the matching flag, waits until its OWN mailbox shows the sequence number of every sender and adds the
+/// slots in rank order (deterministic, identical on all ranks).  Two parities: a rank can be at most one call ahead.
+constexpr int kMaxPeers = 8;
+constexpr int kMailStride = 64;
+constexpr size_t kMailFlagOffset = 2 * kMaxPeers * kMailStride * sizeof(double);
+constexpr size_t kMailBytes = kMailFlagOffset + 2 * kMaxPeers * sizeof(unsigned long long);
+struct CommParams {
+  unsigned char* mail[kMaxPeers];  // mailbox of every rank (mail[rank] is local memory)
+  int world, rank;                 // world <= 1: no exchange
+  unsigned long long seq;          // sequence number of this call (same on all ranks, > 0)
+};
+
 struct LinParams {
   DevTarget tgt;
   DevSource src;
+  CommParams comm;
   double T[12];      // row-major R (9) then t (3): T_target_source of this call
   double Tlin[12];   // pose of the last linearize (error kernel, GICP precision matrix)
   float max_dist_sq;     // search bound in FP32, a hair above the rejector's threshold (FLT_MAX for NullRejector)
@@ -326,6 +343,49 @@ __device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes,
   return best;
 }
 
+/// All-reduce(sum) of one value per thread (threads < NVALS of ONE CTA per rank) over the peer mailboxes -- see CommParams.
+/// Called by ALL threads of the finishing CTA.  A rank whose peers never show up gives up after ~2 s and returns NaN
+/// (a hung collective must not take the GPU down with it).
+template <int NVALS>
+__device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v) {
+  static_assert(NVALS <= kMailStride, "mailbox slot too small");
+  const int tid = threadIdx.x;
+  const size_t par = static_cast<size_t>(c.seq & 1ull);
+  if (tid < NVALS) {
+    for (int p = 0; p < c.world; p++)  // my sums -> slot (par, rank) of every rank's mailbox (remote stores over NVLink)
+      reinterpret_cast<double*>(c.mail[p])[(par * kMaxPeers + c.rank) * kMailStride + tid] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_timeout;
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
+  if (tid < c.world) {
+    __threadfence_system();
+    volatile unsigned long long* theirs = reinterpret_cast<volatile unsigned long long*>(c.mail[tid] + kMailFlagOffset) + par * kMaxPeers + c.rank;
+    *theirs = c.seq;  // publish: rank `tid` may now read my slot
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(c.mail[c.rank] + kMailFlagOffset) + par * kMaxPeers + tid;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*mine != c.seq) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        s_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  double s = 0.0;
+  if (tid < NVALS) {
+    const volatile double* slots = reinterpret_cast<const volatile double*>(c.mail[c.rank]) + par * kMaxPeers * kMailStride;
+    for (int p = 0; p < c.world; p++) s += slots[p * kMailStride + tid];  // rank order: the same sum on every rank
+    if (s_timeout) s = __longlong_as_double(0x7ff8000000000000ll);
+  }
+  return s;
+}
+
 /// CTAs per group of the two-level final reduction (see block_reduce_and_finish)
 constexpr unsigned int kFinishGroup = 16;
 /// doubles / tickets the reduction needs for a grid of `grid` CTAs
@@ -338,8 +398,9 @@ __host__ __device__ inline size_t reduction_tickets(size_t grid) { return 1 + (g
 /// independent L2 loads per lane -- a single CTA adding all gridDim.x partials cost ~15-25 us of an otherwise idle GPU
 /// (profiles/r01/p, r01/t).  The order of the additions depends on gridDim.x only: deterministic.
 /// partials: reduction_partials_doubles(gridDim.x) doubles; ticket: reduction_tickets(gridDim.x) zeroed counters (left zeroed).
+/// comm.world > 1: the finishing CTA then exchanges the sums with the other ranks (comm_all_reduce) before writing `out`.
 template <int NACC, bool EXPAND>
-__device__ __forceinline__ void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out) {
+__device__ __forceinline__ void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out, const CommParams& comm) {
   static_assert(NACC <= 32, "one lane per accumulator");
   __shared__ double s_red[kLinBlock / 32][NACC];
   __shared__ bool s_last;
@@ -389,10 +450,13 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0) ticket[0] = 0u;
+  double v = 0.0;
   if (threadIdx.x < NACC) {  // level 2: the group sums, in group order
-    double v = 0.0;
 #pragma unroll 8
     for (unsigned int gI = 0; gI < n_groups; gI++) v += __ldcg(&group_sums[static_cast<size_t>(gI) * kPartialStride + threadIdx.x]);
+  }
+  if (comm.world > 1) v = comm_all_reduce<NACC>(comm, v);  // level 3: the other GPUs (fused exchange over peer memory)
+  if (threadIdx.x < NACC) {
     if (!EXPAND) {
       out[threadIdx.x] = v;
     } else {

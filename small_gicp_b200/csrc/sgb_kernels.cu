@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kLinBlock) linearize_kd_kernel(const __grid_co
       acc[kAcc] += 1.0;
     }
   }
-  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
+  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
 // Gaussian-voxel-map target (VGICP): hash probe of 1 / 7 / 27 voxels in the reference's offset order
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kLinBlock) linearize_vox_kernel(const __grid_c
     accumulate_factor<ROBUST>(R, M, brx, bry, brz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
     acc[kAcc] += 1.0;
   }
-  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
+  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
 // =============================================================================================
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kLinBlock) error_kernel(const __grid_constant_
     }
     acc[0] += e;
   }
-  block_reduce_and_finish<1, false>(acc, P.partials, P.ticket, P.out);
+  block_reduce_and_finish<1, false>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,6 +271,22 @@ cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool vo
   SGB_DISPATCH(launch_lin, P, voxel, grid, smem, st);
 }
 cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st) { SGB_DISPATCH(launch_err, P, grid, st); }
+
+// A rank whose shard is empty still has to take part in the fused exchange: one CTA that reduces nothing.
+template <int NACC, bool EXPAND>
+__global__ void __launch_bounds__(kLinBlock) reduce_nothing_kernel(const __grid_constant__ LinParams P) {
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; k++) acc[k] = 0.0;
+  block_reduce_and_finish<NACC, EXPAND>(acc, P.partials, P.ticket, P.out, P.comm);
+}
+cudaError_t launch_reduce_nothing(const LinParams& P, bool linearize, cudaStream_t st) {
+  if (linearize)
+    reduce_nothing_kernel<kAcc + 1, true><<<1, kLinBlock, 0, st>>>(P);
+  else
+    reduce_nothing_kernel<1, false><<<1, kLinBlock, 0, st>>>(P);
+  return cudaGetLastError();
+}
 
 int linearize_occupancy(int stack_depth) {
   int nb = 0;

@@ -10,6 +10,7 @@ namespace sgb {
 
 cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool voxel, int grid, int stack_depth, cudaStream_t st);
 cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
+cudaError_t launch_reduce_nothing(const LinParams& P, bool linearize, cudaStream_t st);
 int linearize_occupancy(int stack_depth);
 cudaError_t set_source_curve(int hilbert);
 // sgb_kernels_split.cu

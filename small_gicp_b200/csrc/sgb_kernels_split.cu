@@ -239,7 +239,7 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
     st = st1;
   }
   cp_async_wait_all();
-  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out);
+  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
 template <int FACTOR, int ROBUST>

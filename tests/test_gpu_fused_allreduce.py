@@ -1,0 +1,116 @@
+"""The multi-GPU exchange fused into the reduction kernel (include/sgicp_b200.h sgb_comm_*), exercised on
+ONE GPU: several contexts of one process, each holding a shard of the source on its own stream, wired mailbox to mailbox
+by raw device pointers (the multi-process wiring over CUDA IPC differs only in how the pointers are obtained; bench.py
+--gpus N runs that one).  Every context must end up with the sums of the un-sharded source."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sg():
+    import small_gicp_b200 as sg
+
+    return sg
+
+
+def _pair(n=60_000):
+    from small_gicp_b200.synthetic import make_pair
+
+    tgt, src, T = make_pair(n)
+    scratch = _sg().Context(0)
+    tcov = scratch.estimate_features(tgt, 20, normals=False)[1]
+    scov = scratch.estimate_features(src, 20, normals=False)[1]
+    scratch.close()
+    return tgt, tcov, src, scov, T
+
+
+def _contexts(world, tgt, tcov, src, scov, shards):
+    sg = _sg()
+    ctxs = []
+    for r in range(world):
+        c = sg.Context(0)
+        c.set_target(tgt, None, tcov)
+        c.build_target_kdtree(0)
+        lo, hi = shards[r]
+        c.set_source(src[lo:hi], scov[lo:hi])
+        ctxs.append(c)
+    boxes = [c.comm_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.comm_connect_ptrs(r, world, boxes)
+    return ctxs
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_contexts_exchange_inside_the_kernel(world):
+    import torch
+
+    from small_gicp_b200.distributed import shard_range
+
+    sg = _sg()
+    tgt, tcov, src, scov, T = _pair()
+    n = src.shape[0]
+    full = sg.Context(0)
+    full.set_target(tgt, None, tcov)
+    full.build_target_kdtree(0)
+    full.set_source(src, scov)
+    shards = [shard_range(n, r, world) for r in range(world)]
+    if world == 3:
+        shards = [(0, 0), (0, n // 3), (n // 3, n)]  # an empty shard still takes part in the exchange
+    ctxs = _contexts(world, tgt, tcov, src, scov, shards)
+    outs = [torch.zeros(64, dtype=torch.float64, device="cuda") for _ in range(world)]
+    errs = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+    poses = [np.eye(4), T, T]
+    for it, pose in enumerate(poses):
+        H0, b0, e0 = full.linearize(pose)
+        n0 = full.num_inliers()
+        err0 = full.error(pose)
+        # every launch is asynchronous: rank r's finishing CTA waits (on the device) for the ranks launched after it
+        order = range(world) if it % 2 == 0 else reversed(range(world))
+        for r in order:
+            ctxs[r].linearize_device(pose, outs[r].data_ptr())
+        for r in range(world):
+            ctxs[r].error_device(pose, errs[r].data_ptr())
+        for c in ctxs:
+            c.synchronize()
+        ref = outs[0].cpu().numpy()[:44]
+        assert np.isfinite(ref).all()
+        for r in range(world):
+            h = outs[r].cpu().numpy()[:44]
+            np.testing.assert_array_equal(h, ref)  # summed in rank order on every rank: bit-identical
+            assert float(errs[r].cpu()[0]) == float(errs[0].cpu()[0])
+        H, b, e, ninl = ref[:36].reshape(6, 6), ref[36:42], ref[42], ref[43]
+        # shards re-centre their own source boxes: FP32 roundings differ slightly from the un-sharded run
+        assert np.linalg.norm(H - H0) <= 1e-5 * np.linalg.norm(H0)
+        assert abs(e - e0) <= 1e-5 * e0 and abs(float(errs[0].cpu()[0]) - err0) <= 1e-5 * err0
+        assert abs(ninl - n0) <= 3
+        scale = np.sqrt(2.0 * e0 * np.diag(H0))
+        assert np.all(np.abs(b - b0) <= 1e-5 * scale)
+    # after disconnect a context is single-GPU again
+    ctxs[-1].comm_disconnect()
+    lo, hi = shards[-1]
+    Hs, bs, es = ctxs[-1].linearize(T)
+    solo = sg.Context(0)
+    solo.set_target(tgt, None, tcov)
+    solo.build_target_kdtree(0)
+    solo.set_source(src[lo:hi], scov[lo:hi])
+    H1, b1, e1 = solo.linearize(T)
+    assert np.array_equal(Hs, H1) and es == e1
+    for c in ctxs + [full, solo]:
+        c.close()
+
+
+def test_missing_peer_times_out_instead_of_hanging():
+    """A collective whose peer never arrives must not hang the GPU: the waiting CTA gives up after ~2 s and returns NaN."""
+    import torch
+
+    sg = _sg()
+    tgt, tcov, src, scov, T = _pair(20_000)
+    n = src.shape[0]
+    ctxs = _contexts(2, tgt, tcov, src, scov, [(0, n // 2), (n // 2, n)])
+    out = torch.zeros(64, dtype=torch.float64, device="cuda")
+    ctxs[0].linearize_device(T, out.data_ptr())  # rank 1 never calls
+    ctxs[0].synchronize()
+    assert np.isnan(out.cpu().numpy()[:44]).all()
+    for c in ctxs:
+        c.close()
