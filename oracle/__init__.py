@@ -99,9 +99,7 @@ def reference_lib():
         if not os.path.exists(path):
             return None
         L = C.CDLL(path)
-        base = lib()
-        for name in dir(base):
-            pass
+        lib()  # fills _SIGNATURES
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -111,6 +111,7 @@ int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
     P.comm.rank = ctx->comm_rank;
     for (int p = 0; p < ctx->comm_world; p++) P.comm.mail[p] = ctx->comm_peers[p];
     P.comm.seq = ++ctx->comm_seq;  // exactly one reduction per fill_params (do_linearize / do_error)
+    P.comm.timeout_ns = ctx->comm_timeout_ns;
   }
   return 0;
 }
@@ -333,6 +334,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
     if (v > 0.1 && v < 100.0) ctx->grid_cell_factor = v;
   }
   ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
+  if (const char* s = getenv("SGB_COMM_TIMEOUT_MS")) ctx->comm_timeout_ns = static_cast<unsigned long long>(std::max(1, atoi(s))) * 1000000ull;
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
     ctx->host_tree = (s[0] == 'h');
     if (s[0] == 'l') ctx->tree_quality = 0;

@@ -94,6 +94,7 @@ struct sgb_ctx {
   bool comm_ipc_opened[8] = {};           // mapped by cudaIpcOpenMemHandle (to be closed)
   int comm_world = 0, comm_rank = 0;      // world <= 1: single GPU
   unsigned long long comm_seq = 0;        // collective calls issued so far
+  unsigned long long comm_timeout_ns = 5000000000ull;  // a peer that has not arrived after 5 s (SGB_COMM_TIMEOUT_MS) is given up on
 
   // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
   bool have_lin = false;

@@ -54,6 +54,7 @@ struct CommParams {
   unsigned char* mail[kMaxPeers];  // mailbox of every rank (mail[rank] is local memory)
   int world, rank;                 // world <= 1: no exchange
   unsigned long long seq;          // sequence number of this call (same on all ranks, > 0)
+  unsigned long long timeout_ns;   // give up waiting for a peer after this long (the result is then NaN)
 };
 
 struct LinParams {
@@ -344,7 +345,7 @@ __device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes,
 }
 
 /// All-reduce(sum) of one value per thread (threads < NVALS of ONE CTA per rank) over the peer mailboxes -- see CommParams.
-/// Called by ALL threads of the finishing CTA.  A rank whose peers never show up gives up after ~2 s and returns NaN
+/// Called by ALL threads of the finishing CTA.  A rank whose peers never show up gives up after c.timeout_ns and returns NaN
 /// (a hung collective must not take the GPU down with it).
 template <int NVALS>
 __device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v) {
@@ -369,7 +370,7 @@ __device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*mine != c.seq) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ull) {
+      if (t1 - t0 > c.timeout_ns) {
         s_timeout = 1;
         break;
       }

@@ -100,13 +100,14 @@ def test_sharded_contexts_exchange_inside_the_kernel(world):
         c.close()
 
 
-def test_missing_peer_times_out_instead_of_hanging():
-    """A collective whose peer never arrives must not hang the GPU: the waiting CTA gives up after ~2 s and returns NaN."""
+def test_missing_peer_times_out_instead_of_hanging(monkeypatch):
+    """A collective whose peer never arrives must not hang the GPU: the waiting CTA gives up (here after 300 ms) and returns NaN."""
     import torch
 
     sg = _sg()
     tgt, tcov, src, scov, T = _pair(20_000)
     n = src.shape[0]
+    monkeypatch.setenv("SGB_COMM_TIMEOUT_MS", "300")
     ctxs = _contexts(2, tgt, tcov, src, scov, [(0, n // 2), (n // 2, n)])
     out = torch.zeros(64, dtype=torch.float64, device="cuda")
     ctxs[0].linearize_device(T, out.data_ptr())  # rank 1 never calls
