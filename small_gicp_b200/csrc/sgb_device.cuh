@@ -73,6 +73,11 @@ struct LinParams {
   double* out;        // 44 doubles: H(36) | b(6) | e | num_inliers     (error kernel: out[0] = e)
 };
 
+/// Programmatic dependent launch (sm_90+).  A kernel launched with launch_dependent() (sgb_kernels.h) may be set up and
+/// scheduled while its predecessor on the stream is still draining; it must call this before it touches anything the
+/// predecessor wrote.  Without the launch attribute the instruction returns immediately.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vox_hash(int x, int y, int z) {
   // any hash works (lookups are exact-match); this is a 32-bit mix of the three coordinates

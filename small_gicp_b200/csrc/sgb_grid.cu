@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
                                                                    const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell) {
   __shared__ uint2 s_desc[kPendWarps][kPendStack];
   __shared__ float s_dist[kPendWarps][kPendStack];
+  grid_dependency_wait();  // the probe filled the pending list
   const uint32_t count = *pending_count;
   if (count > max_pending) return;
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -509,9 +510,8 @@ cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int 
                                   cudaStream_t st) {
   if (depth > kPendStack) return cudaErrorInvalidValue;
   // block_table: the block-list table (enables the ring phase) or null
-  pending_search_kernel<<<grid, kLinBlock, 0, st>>>(P, pnodes, pending_count, pending_list, max_pending, grid_pts, block_table, capacity - 1u, g,
-                                                    1.0f / g.inv_cell);
-  return cudaGetLastError();
+  return launch_dependent(pending_search_kernel, grid, kLinBlock, 0, st, P, pnodes, pending_count, pending_list, max_pending, grid_pts, block_table, capacity - 1u, g,
+                          1.0f / g.inv_cell);
 }
 
 }  // namespace sgb

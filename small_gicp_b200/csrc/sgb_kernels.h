@@ -4,9 +4,32 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "sgb_device.cuh"
 
 namespace sgb {
+
+/// Launch `kernel` as a programmatic dependent of the previous kernel on `st` (its set-up overlaps the predecessor's tail;
+/// the kernel itself waits with grid_dependency_wait()).  SGB_PDL=0 falls back to plain stream order (A/B switch).
+inline bool pdl_enabled() {
+  static const bool on = !(std::getenv("SGB_PDL") && std::getenv("SGB_PDL")[0] == '0');
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 cudaError_t launch_linearize(const LinParams& P, int factor, int robust, bool voxel, int grid, int stack_depth, cudaStream_t st);
 cudaError_t launch_error(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);

@@ -34,6 +34,7 @@ __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const f
 __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
                                                                   const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
                                                                   uint32_t min_pending) {
+  grid_dependency_wait();  // probe / pending search wrote corr[], the settled flags and the pending counter
   // with the grid front end this kernel only runs when MANY queries are pending (misaligned first iterations); a handful
   // of scattered pending queries is served by pending_search_kernel instead
   if (pending_count && *pending_count <= min_pending) return;
@@ -205,8 +206,11 @@ cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int g
                                  uint32_t min_pending, cudaStream_t st) {
   if (max_depth > 40) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
-  packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending);
-  return cudaGetLastError();
+  if (!settled) {  // no grid front end: nothing on the stream this launch could overlap with
+    packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending);
+    return cudaGetLastError();
+  }
+  return launch_dependent(packet_search_kernel, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending);
 }
 
 }  // namespace sgb

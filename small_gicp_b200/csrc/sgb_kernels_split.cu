@@ -193,6 +193,7 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
     }
   };
 
+  grid_dependency_wait();  // the search kernels wrote the correspondences
   const uint32_t G = gridDim.x;
   uint32_t tile = blockIdx.x;
   issue_a(tile, 0);
@@ -245,8 +246,7 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
 template <int FACTOR, int ROBUST>
 static cudaError_t launch_factor(const LinParams& P, int grid, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
-  factor_reduce_kernel<FACTOR, ROBUST><<<grid, kLinBlock, smem, st>>>(P);
-  return cudaGetLastError();
+  return launch_dependent(factor_reduce_kernel<FACTOR, ROBUST>, grid, kLinBlock, smem, st, P);
 }
 
 // resident CTAs per SM of one instantiation (the grid is sized to exactly one wave: a partial second wave of this
