@@ -95,6 +95,17 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size);
  * search_offsets is 1, 7 or 27 (:157-186). */
 int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, const int32_t* coords_xyz, const double* means_xyz1,
                             const double* covs_4x4, int search_offsets);
+/* Build the Gaussian voxel map on the device from raw points (+ 4x4 covariances): replaces the one-shot use of
+ * IncrementalVoxelMap<GaussianVoxel>::insert (ann/incremental_voxelmap.hpp:55-92) with GaussianVoxel::add / finalize
+ * (ann/gaussian_voxelmap.hpp:30-62): voxel = floor(p / leaf_size), mean = sum p / n, cov = sum C / n.  Voxel ids are in
+ * ascending key order (the reference numbers them in first-insertion order; only the ids differ). */
+int sgb_target_build_voxelmap(sgb_ctx* ctx, size_t n, const double* points_xyz1, const double* covs_4x4 /*or NULL*/, double leaf_size,
+                              int search_offsets);
+/* k nearest neighbours (1 <= k <= 32) of arbitrary query points in the target's kd-tree: replaces KdTree::knn_search /
+ * nearest_neighbor_search (ann/kdtree.hpp:165-189,254-274) and the batch_knn_search / batch_nearest_neighbor_search of the
+ * Python binding (src/python/kdtree.cpp).  out_indices / out_sq_dists: n_queries x k, ascending distance, original target
+ * indices; UINT64_MAX / DBL_MAX pad when the target has fewer than k points (knn_result.hpp:60-66). */
+int sgb_target_batch_knn(sgb_ctx* ctx, size_t n_queries, const double* queries_xyz1, int k, uint64_t* out_indices, double* out_sq_dists);
 size_t sgb_target_size(const sgb_ctx* ctx);
 
 /* ---- source: replaces traits::point/cov(source, i) ------------------------------------------- */

@@ -35,6 +35,8 @@ _SIGNATURES = {
     "sgb_target_set_kdtree": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _u64p]),
     "sgb_target_build_kdtree": (C.c_int, [_vp, C.c_int]),
     "sgb_target_set_voxelmap": (C.c_int, [_vp, C.c_double, C.c_size_t, _i32p, _dp, _dp, C.c_int]),
+    "sgb_target_build_voxelmap": (C.c_int, [_vp, C.c_size_t, _dp, _dp, C.c_double, C.c_int]),
+    "sgb_target_batch_knn": (C.c_int, [_vp, C.c_size_t, _dp, C.c_int, _u64p, _dp]),
     "sgb_target_size": (C.c_size_t, [_vp]),
     "sgb_source_set_points": (C.c_int, [_vp, C.c_size_t, _dp, _dp]),
     "sgb_source_size": (C.c_size_t, [_vp]),
@@ -168,6 +170,22 @@ class Context:
         m = _points4(means)
         c = _f64(covs) if covs is not None else None
         self._check(self._L.sgb_target_set_voxelmap(self._h, float(leaf_size), m.shape[0], coords.ctypes.data_as(_i32p), _d(m), _d(c), int(search_offsets)))
+
+    def build_target_voxelmap(self, points, covs, leaf_size, search_offsets=1):
+        """GaussianVoxelMap(leaf_size).insert(points) built on the device (incremental_voxelmap.hpp:55-92)"""
+        p = _points4(points)
+        c = _f64(covs) if covs is not None else None
+        if c is not None:
+            assert c.shape == (p.shape[0], 4, 4)
+        self._check(self._L.sgb_target_build_voxelmap(self._h, p.shape[0], _d(p), _d(c), float(leaf_size), int(search_offsets)))
+
+    def target_batch_knn(self, queries, k=1):
+        """KdTree.batch_knn_search(queries, k) on the device -> (indices (N,k) uint64, squared distances (N,k))"""
+        q = _points4(queries)
+        idx = np.empty((q.shape[0], int(k)), dtype=np.uint64)
+        d = np.empty((q.shape[0], int(k)))
+        self._check(self._L.sgb_target_batch_knn(self._h, q.shape[0], _d(q), int(k), idx.ctypes.data_as(_u64p), _d(d)))
+        return idx, d
 
     @property
     def target_size(self):

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "../../include/sgicp_b200.h"
@@ -256,6 +257,112 @@ int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points, double 
     CU(cudaStreamSynchronize(ctx->stream));
   }
   *n_out = count;
+  return 0;
+}
+
+// Gaussian voxel map built on the device: replaces IncrementalVoxelMap<GaussianVoxel>::insert
+// (incremental_voxelmap.hpp:55-92) + GaussianVoxel::add / finalize (gaussian_voxelmap.hpp:30-62) for a one-shot map.
+int sgb_target_build_voxelmap(sgb_ctx* ctx, size_t n, const double* points, const double* covs, double leaf_size, int search_offsets) {
+  if (!ctx) return 1;
+  if (!(leaf_size > 0.0)) return fail(ctx, 1, "sgb_target_build_voxelmap: leaf_size must be positive");
+  if (n && !points) return fail(ctx, 1, "sgb_target_build_voxelmap: null points");
+  if (n >= (1ull << 31)) return fail(ctx, 1, "sgb_target_build_voxelmap: too many points");
+  if (search_offsets != 1 && search_offsets != 7 && search_offsets != 27) search_offsets = 1;  // incremental_voxelmap.hpp:159-163
+  CU(cudaSetDevice(ctx->device));
+  ctx->tgt_has_normals = false;
+  ctx->tgt_has_covs = covs != nullptr;
+  ctx->tgt_is_voxel = true;
+  ctx->tgt_has_kd = false;
+  ctx->grid_ready = false;
+  ctx->tgt_ready = true;
+  ctx->have_lin = false;
+  ctx->corr_seeds = false;
+  ctx->vox_offsets = search_offsets;
+  ctx->vox_inv_leaf = 1.0 / leaf_size;
+  ctx->n_tgt = 0;
+  CU(ctx->tgt_centre.reserve(4 * sizeof(double)));
+  CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
+  if (n == 0) return 0;
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (covs) {
+    CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
+  CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
+  CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_vals_out.reserve(n * sizeof(uint32_t)));
+  CU(ctx->pre_heads.reserve((n + 1) * sizeof(uint32_t)));
+  CU(ctx->pre_slots.reserve((n + 1) * sizeof(uint32_t)));
+  CU(launch_voxel_keys(ctx->stage_pts.as<double>(), n, 1.0 / leaf_size, ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  size_t temp_bytes = 0, scan_bytes = 0;
+  CU(sort_pairs_u64_u32(nullptr, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->pre_vals_out.as<uint32_t>(), n, ctx->stream));
+  CU(exclusive_sum_u32(nullptr, scan_bytes, ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n + 1, ctx->stream));
+  CU(ctx->sort_temp.reserve(temp_bytes > scan_bytes ? temp_bytes : scan_bytes));
+  CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
+                        ctx->pre_vals_out.as<uint32_t>(), n, ctx->stream));
+  CU(cudaMemsetAsync(ctx->pre_heads.p, 0, (n + 1) * sizeof(uint32_t), ctx->stream));
+  CU(launch_voxel_heads(ctx->keys_out.as<uint64_t>(), n, ctx->pre_heads.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  CU(exclusive_sum_u32(ctx->sort_temp.p, scan_bytes, ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n + 1, ctx->stream));
+  uint32_t n_vox = 0;
+  CU(cudaMemcpyAsync(&n_vox, ctx->pre_slots.as<uint32_t>() + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 7;
+  if (n_vox == 0) return 0;  // every point outside the 21-bit voxel range
+  // per-voxel mean / covariance / integer coordinates (FP64), then the same device-side conversion as sgb_target_set_voxelmap
+  CU(ctx->pre_out_normals.reserve(static_cast<size_t>(n_vox) * 4 * sizeof(double)));
+  if (covs) CU(ctx->pre_out_covs.reserve(static_cast<size_t>(n_vox) * 16 * sizeof(double)));
+  CU(ctx->tmp_pts.reserve(static_cast<size_t>(n_vox) * sizeof(int4)));
+  CU(launch_voxel_stats(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n,
+                        ctx->stage_pts.as<double>(), covs ? ctx->stage_covs.as<double>() : nullptr, ctx->pre_out_normals.as<double>(),
+                        covs ? ctx->pre_out_covs.as<double>() : nullptr, ctx->tmp_pts.as<int4>(), ctx->sm_count, ctx->stream));
+  CU(ctx->tgt_pts.reserve(static_cast<size_t>(n_vox) * sizeof(float4)));
+  if (covs) {
+    CU(ctx->tgt_covA.reserve(static_cast<size_t>(n_vox) * sizeof(float4)));
+    CU(ctx->tgt_covB.reserve(static_cast<size_t>(n_vox) * sizeof(float4)));
+  }
+  CU(launch_bounds_centre(ctx->pre_out_normals.as<double>(), n_vox, ctx->tgt_bounds.as<double>(), ctx->tgt_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->pre_out_normals.as<double>(), nullptr, covs ? ctx->pre_out_covs.as<double>() : nullptr, n_vox, ctx->tgt_centre.as<double>(),
+                    ctx->tgt_pts.as<float4>(), nullptr, ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->sm_count, ctx->stream));
+  uint32_t capacity = 16;
+  while (capacity < 2ull * n_vox) capacity <<= 1;  // load factor <= 1/2
+  CU(ctx->vox_table.reserve(static_cast<size_t>(capacity) * sizeof(int4)));
+  CU(launch_vox_table_build(ctx->tmp_pts.as<int4>(), n_vox, ctx->vox_table.as<int4>(), capacity, ctx->stream));
+  ctx->launches += 7;
+  ctx->vox_mask = capacity - 1;
+  ctx->n_tgt = n_vox;
+  return 0;
+}
+
+// k nearest neighbours of arbitrary queries in the target's search structure (the batch NN API)
+int sgb_target_batch_knn(sgb_ctx* ctx, size_t n_queries, const double* queries, int k, uint64_t* out_indices, double* out_sq_dists) {
+  if (!ctx) return 1;
+  if (k < 1 || k > 32) return fail(ctx, 1, "sgb_target_batch_knn: k must be in 1..32");
+  if (n_queries && (!queries || !out_indices || !out_sq_dists)) return fail(ctx, 1, "sgb_target_batch_knn: null buffer");
+  if (n_queries >= (1ull << 31) / static_cast<size_t>(k)) return fail(ctx, 1, "sgb_target_batch_knn: too many queries");
+  if (ctx->tgt_is_voxel || !ctx->tgt_ready) return fail(ctx, 1, "sgb_target_batch_knn: needs a point target with its kd-tree (set points, then set/build the tree)");
+  if (n_queries == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = n_queries, nk = n * static_cast<size_t>(k);
+  if (ctx->n_tgt == 0) {  // nothing to find: KnnResult's initial state
+    for (size_t j = 0; j < nk; j++) {
+      out_indices[j] = ~0ull;
+      out_sq_dists[j] = std::numeric_limits<double>::max();
+    }
+    return 0;
+  }
+  CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, queries, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->pre_out_covs.reserve(nk * sizeof(double)));
+  CU(ctx->corr64.reserve(nk * sizeof(uint64_t)));
+  CU(launch_batch_knn(ctx->tgt_pnodes.as<float4>(), ctx->tgt_pts.as<float4>(), ctx->stage_pts.as<double>(), static_cast<uint32_t>(n), k, ctx->tgt_centre.as<double>(),
+                      ctx->corr64.as<unsigned long long>(), ctx->pre_out_covs.as<double>(), ctx->tree_depth, ctx->stream));
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(out_indices, ctx->corr64.p, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_sq_dists, ctx->pre_out_covs.p, nk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -353,9 +353,39 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
         const float ez = fmaxf(fmaxf(static_cast<float>(bz) - uz, uz - static_cast<float>(bz + 2)) - kGridSlack, 0.0f);
         if ((ex * ex + ey * ey + ez * ez) * cell * cell < best_d) e = grid_lookup(table, mask, bx, by, bz);
       }
+      // The (typically ~9 non-empty) lists are scanned as ONE flattened run spread over all 32 lanes: point j of the
+      // concatenation goes to lane j mod 32, which finds its list by a shuffle binary search over the exclusive prefix
+      // sums of the counts.  A lane per list would walk up to ~40 points in dependent batches; this is ~7 loads per lane.
+      uint32_t incl = e.y;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= static_cast<uint32_t>(o)) incl += t;
+      }
+      const uint32_t excl = incl - e.y, total = __shfl_sync(0xffffffffu, incl, 31);
       float my_d = best_d;
       uint32_t my_best = kNone;
-      grid_scan(grid_pts + e.x, e.y, qx, qy, qz, my_d, my_best);
+#pragma unroll 2
+      for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t j = base + lane;
+        uint32_t owner = 0;  // largest lane whose exclusive prefix is <= j (empty lists share their successor's prefix and lose)
+#pragma unroll
+        for (uint32_t step = 16u; step >= 1u; step >>= 1) {
+          const uint32_t cand = owner + step;
+          const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
+          if (cand < 32u && ex <= j) owner = cand;
+        }
+        const uint32_t st = __shfl_sync(0xffffffffu, e.x, owner), ex0 = __shfl_sync(0xffffffffu, excl, owner);
+        if (j < total) {
+          const float4 t = __ldg(&grid_pts[st + (j - ex0)]);
+          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < my_d) {
+            my_d = d;
+            my_best = __float_as_uint(t.w);
+          }
+        }
+      }
       const uint32_t dbits = my_best != kNone ? __float_as_uint(my_d) : 0x7f800000u;
       const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
       if (dmin != 0x7f800000u) {

@@ -275,6 +275,65 @@ cudaError_t launch_features(const float4* nodes, const float4* pts, uint32_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// k-NN of arbitrary query points in the target's search structure (KdTree::knn_search, ann/kdtree.hpp:165-189;
+// batch_knn_search / batch_nearest_neighbor_search of the Python binding): one query per thread, results ascending.
+// The search runs on the FP32 centred coordinates; the reported squared distances are recomputed in FP64.
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(kLinBlock) batch_knn_kernel(const float4* __restrict__ pnodes, const float4* __restrict__ pts, const double4* __restrict__ queries,
+                                                              uint32_t n, int k, const double* __restrict__ centre, unsigned long long* out_idx, double* out_d,
+                                                              int depth) {
+  extern __shared__ uint2 s_stack[];  // [depth][kLinBlock] descriptors, then [depth][kLinBlock] distances
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 q = queries[i];
+  const double qx = q.x - centre[0], qy = q.y - centre[1], qz = q.z - centre[2];
+  KnnList<KMAX> L;
+  L.init(k);
+  bvh_knn<KMAX>(pnodes, pts, static_cast<float>(qx), static_cast<float>(qy), static_cast<float>(qz), L, s_stack,
+                reinterpret_cast<float*>(s_stack + static_cast<size_t>(depth) * kLinBlock));
+#pragma unroll
+  for (int j = 0; j < KMAX; j++) {
+    if (j < k) {
+      unsigned long long idx = ~0ull;  // fewer than k points: size_t(-1) / max() like KnnResult's initial state (knn_result.hpp:60-66)
+      double d = DBL_MAX;
+      if (L.i[j] != kNone) {
+        const float4 t = __ldg(&pts[L.i[j]]);
+        const double dx = static_cast<double>(t.x) - qx, dy = static_cast<double>(t.y) - qy, dz = static_cast<double>(t.z) - qz;
+        idx = static_cast<uint32_t>(__float_as_int(t.w));
+        d = dx * dx + dy * dy + dz * dz;
+      }
+      out_idx[static_cast<size_t>(i) * k + j] = idx;
+      out_d[static_cast<size_t>(i) * k + j] = d;
+    }
+  }
+}
+
+template <int KMAX>
+static cudaError_t launch_batch_knn_t(const float4* pnodes, const float4* pts, const double* queries4, uint32_t n, int k, const double* centre,
+                                      unsigned long long* out_idx, double* out_d, int depth, cudaStream_t st) {
+  if (depth < 1) depth = 1;
+  const size_t smem = static_cast<size_t>(depth) * kLinBlock * (sizeof(uint2) + sizeof(float));
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(batch_knn_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  batch_knn_kernel<KMAX><<<(n + kLinBlock - 1) / kLinBlock, kLinBlock, smem, st>>>(pnodes, pts, reinterpret_cast<const double4*>(queries4), n, k, centre, out_idx,
+                                                                                  out_d, depth);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_batch_knn(const float4* pnodes, const float4* pts, const double* queries4, uint32_t n, int k, const double* centre, unsigned long long* out_idx,
+                             double* out_d, int depth, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (k <= 1) return launch_batch_knn_t<1>(pnodes, pts, queries4, n, k, centre, out_idx, out_d, depth, st);
+  if (k <= 10) return launch_batch_knn_t<10>(pnodes, pts, queries4, n, k, centre, out_idx, out_d, depth, st);
+  if (k <= 20) return launch_batch_knn_t<20>(pnodes, pts, queries4, n, k, centre, out_idx, out_d, depth, st);
+  if (k <= 32) return launch_batch_knn_t<32>(pnodes, pts, queries4, n, k, centre, out_idx, out_d, depth, st);
+  return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
 // voxel-grid down-sampling
 // ---------------------------------------------------------------------------------------------
 __global__ void voxel_keys_kernel(const double4* __restrict__ pts, size_t n, double inv_leaf, uint64_t* keys, uint32_t* vals) {
@@ -340,6 +399,83 @@ cudaError_t launch_voxel_means(const uint64_t* keys, const uint32_t* vals, const
                                                              reinterpret_cast<double4*>(d_out4));
   return cudaGetLastError();
 }
+// ---------------------------------------------------------------------------------------------
+// Gaussian voxel map construction (incremental_voxelmap.hpp:55-92 with GaussianVoxel::add / finalize,
+// gaussian_voxelmap.hpp:30-62): one thread per voxel adds its points and covariances in original-index order
+// (the order the reference's insert loop meets them) and divides by the count.
+// ---------------------------------------------------------------------------------------------
+__global__ void voxel_stats_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ heads,
+                                   const uint32_t* __restrict__ slots, size_t n, const double4* __restrict__ pts, const double* __restrict__ covs,
+                                   double4* out_means, double* out_covs, int4* out_coords) {
+  constexpr int coord_bit_size = 21;
+  constexpr uint64_t coord_bit_mask = (1ull << 21) - 1;
+  constexpr int coord_offset = 1 << (coord_bit_size - 1);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (!heads[i]) continue;
+    const uint64_t k = keys[i];
+    double sx = 0, sy = 0, sz = 0, cnt = 0;
+    double c[16];
+#pragma unroll
+    for (int a = 0; a < 16; a++) c[a] = 0.0;
+    for (size_t j = i; j < n && keys[j] == k; j++) {
+      const uint32_t v = vals[j];
+      const double4 p = pts[v];
+      sx += p.x;
+      sy += p.y;
+      sz += p.z;
+      cnt += 1.0;
+      if (covs) {
+        const double* cv = covs + static_cast<size_t>(v) * 16;
+#pragma unroll
+        for (int a = 0; a < 16; a++) c[a] += cv[a];
+      }
+    }
+    const uint32_t id = slots[i];
+    out_means[id] = make_double4(sx / cnt, sy / cnt, sz / cnt, 1.0);
+    if (covs) {
+#pragma unroll
+      for (int a = 0; a < 16; a++) out_covs[static_cast<size_t>(id) * 16 + a] = c[a] / cnt;
+    }
+    out_coords[id] = make_int4(static_cast<int>(k & coord_bit_mask) - coord_offset, static_cast<int>((k >> coord_bit_size) & coord_bit_mask) - coord_offset,
+                               static_cast<int>((k >> (2 * coord_bit_size)) & coord_bit_mask) - coord_offset, static_cast<int>(id));
+  }
+}
+
+__global__ void vox_table_clear_kernel(int4* table, uint32_t capacity) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < capacity) table[i] = make_int4(0, 0, 0, -1);
+}
+
+// voxel coordinates are distinct, so an insert only has to find a free slot of its probe sequence
+__global__ void vox_table_insert_kernel(const int4* __restrict__ coords, uint32_t n_voxels, int4* table, uint32_t mask) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_voxels) return;
+  const int4 c = coords[i];
+  uint32_t slot = vox_hash(c.x, c.y, c.z) & mask;
+  for (;;) {
+    if (atomicCAS(&table[slot].w, -1, c.w) == -1) {
+      table[slot].x = c.x;
+      table[slot].y = c.y;
+      table[slot].z = c.z;
+      return;
+    }
+    slot = (slot + 1u) & mask;
+  }
+}
+
+cudaError_t launch_voxel_stats(const uint64_t* keys, const uint32_t* vals, const uint32_t* heads, const uint32_t* slots, size_t n, const double* d_pts4,
+                               const double* d_covs16, double* out_means4, double* out_covs16, int4* out_coords, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  voxel_stats_kernel<<<vgrid(n, sm_count * 8), 256, 0, st>>>(keys, vals, heads, slots, n, reinterpret_cast<const double4*>(d_pts4), d_covs16,
+                                                             reinterpret_cast<double4*>(out_means4), out_covs16, out_coords);
+  return cudaGetLastError();
+}
+cudaError_t launch_vox_table_build(const int4* coords, uint32_t n_voxels, int4* table, uint32_t capacity, cudaStream_t st) {
+  vox_table_clear_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
+  if (n_voxels) vox_table_insert_kernel<<<(n_voxels + 255u) / 256u, 256, 0, st>>>(coords, n_voxels, table, capacity - 1u);
+  return cudaGetLastError();
+}
+
 cudaError_t exclusive_sum_u32(void* d_temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
   return cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, in, out, static_cast<int>(n), st);
 }

@@ -210,6 +210,46 @@ def test_voxelmap_target(golden_prepared):
         ctx.close()
 
 
+def test_device_built_voxelmap_matches_oracle(golden_prepared):
+    """sgb_target_build_voxelmap (voxel keys -> radix sort -> per-voxel mean / covariance -> hash table, all on the device)
+    against the oracle's restatement of IncrementalVoxelMap<GaussianVoxel>::insert: same set of voxels, same means and
+    covariances, and the same VGICP sums (voxel ids are numbered differently, so correspondences are compared by voxel)."""
+    g = golden_prepared
+    sg = _sg()
+    tgt = g["target"]
+    for leaf, offsets in ((1.0, 1), (0.5, 7), (2.0, 27)):
+        vm = O.GaussianVoxelMap(tgt, leaf, offsets)
+        coords, means, covs, _ = vm.export()
+        adopted = sg.Context(0)
+        adopted.set_target_voxelmap(leaf, coords, means, covs, offsets)
+        built = sg.Context(0)
+        built.build_target_voxelmap(tgt.points, tgt.covs, leaf, offsets)
+        assert built.target_size == len(coords)
+        for ctx in (adopted, built):
+            ctx.set_source(g["source"].points, g["source"].covs)
+        # the ids differ (ascending key order vs first-insertion order): map both to voxel coordinates
+        order_ref = {tuple(int(v) for v in c): i for i, c in enumerate(coords)}
+        keys_sorted = sorted(order_ref, key=lambda c: ((c[2] + (1 << 20)) << 42) | ((c[1] + (1 << 20)) << 21) | (c[0] + (1 << 20)))
+        id_built_to_ref = np.array([order_ref[c] for c in keys_sorted], dtype=np.int64)
+        for T in (np.eye(4), g["T"]):
+            Ha, ba, ea = adopted.linearize(T, factor=sg.FACTOR_GICP)
+            Hb, bb, eb = built.linearize(T, factor=sg.FACTOR_GICP)
+            assert np.linalg.norm(Ha - Hb) <= 1e-9 * np.linalg.norm(Ha) and abs(ea - eb) <= 1e-9 * ea, (leaf, offsets)
+            ca, cb = adopted.correspondences(), built.correspondences()
+            none = ca == sg.NO_CORRESPONDENCE
+            assert np.array_equal(none, cb == sg.NO_CORRESPONDENCE)
+            ida = (ca[~none] >> np.uint64(32)).astype(np.int64)
+            idb = (cb[~none] >> np.uint64(32)).astype(np.int64)
+            assert np.array_equal(ida, id_built_to_ref[idb])
+        adopted.close()
+        built.close()
+    # empty input and points outside the 21-bit voxel range
+    ctx = sg.Context(0)
+    ctx.build_target_voxelmap(np.zeros((0, 4)), None, 1.0)
+    assert ctx.target_size == 0
+    ctx.close()
+
+
 def test_empty_and_tiny_inputs(golden_prepared):
     g = golden_prepared
     sg = _sg()

@@ -111,3 +111,40 @@ def test_device_resident_pipeline(golden):
         assert np.array_equal(a.correspondences(), b.correspondences())
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("k", [1, 5, 20, 32])
+def test_batch_knn_matches_oracle(golden, k):
+    """sgb_target_batch_knn against the oracle's restatement of UnsafeKdTree::knn_search (ann/kdtree.hpp:165-233): the same
+    neighbours in the same order (FP32 near-ties verified by distance), squared distances to FP32 storage accuracy --
+    kdtree_test.cpp:81-105 semantics with arbitrary (off-cloud) queries."""
+    import small_gicp_b200 as sg
+
+    tgt, src, T = golden
+    cloud = O.Cloud(tgt).voxelgrid_sampling(0.25)
+    tree = O.KdTree(cloud)
+    rng = np.random.default_rng(3)
+    queries = np.concatenate([src[:4000] @ T[:3, :3].T + T[:3, 3], cloud.points[:500, :3], rng.uniform(-60, 60, (300, 3))])
+    ridx, rd2, rcnt = tree.knn(queries, k, max(1, O.max_threads()))
+    for own in (True, False):
+        c = sg.Context(0)
+        c.set_target(cloud.points)
+        if own:
+            c.build_target_kdtree(0)
+        else:
+            c.set_target_kdtree(*tree.export())
+        idx, d2 = c.target_batch_knn(queries, k)
+        c.close()
+        assert idx.shape == (len(queries), k) and np.all(np.diff(d2, axis=1) >= 0)
+        np.testing.assert_allclose(d2, rd2, rtol=2e-5, atol=1e-9)
+        differ = idx != ridx
+        assert differ.mean() < 2e-3
+        # where the order differs the distances are (FP32-)tied
+        assert np.all(np.abs(d2[differ] - rd2[differ]) <= 2e-5 * rd2[differ] + 1e-9)
+    # fewer target points than k: padded like KnnResult's initial state
+    c = sg.Context(0)
+    c.set_target(cloud.points[:3])
+    c.build_target_kdtree(0)
+    idx, d2 = c.target_batch_knn(queries[:10], 5)
+    c.close()
+    assert np.all(idx[:, 3:] == np.uint64(0xFFFFFFFFFFFFFFFF)) and np.all(idx[:, :3] < 3)
