@@ -2,16 +2,21 @@
 // Uniform-grid front end of the exact nearest-neighbour search.
 //
 // In a registration that is not wildly misaligned almost every query's nearest neighbour is a fraction of the point
-// spacing away.  For such a query a hash probe of the 2 x 2 x 2 block of grid cells (cell edge c) that covers the cube
-// [q - c/2, q + c/2]^3 sees EVERY target point within c/2 of q, so if the closest point found is within c/2 it is the
-// exact nearest neighbour and the query is finished: a hash lookup or three + a few dozen distance tests, no tree walk,
-// no dependent pointer chasing.  The query's own cell is scanned first; each of the other seven cells of the block is
-// looked up only if its box is still closer than the best distance so far (usually one or two are).
-// Queries it cannot settle (nothing within c/2: misaligned first iterations, holes, outliers) are appended to a compact
-// pending list -- with the best candidate found so far as an upper bound -- and finished exactly by a tree search:
-// a warp per pending query when they are few (pending_search_kernel below), the packet search (sgb_kernels_packet.cu)
-// when they are many.  Results are therefore identical to a pure tree search (exact ties aside); ncu evidence and the
-// A/B switch (SGB_GRID=0) are recorded in profiles/.
+// spacing away.  The 2 x 2 x 2 block of grid cells (cell edge c) anchored at floor(u - 1/2) covers the cube
+// [q - c/2, q + c/2]^3, i.e. it holds EVERY target point within c/2 of q: if the closest point of the block is within c/2
+// it is the exact nearest neighbour and the query is finished -- no tree walk, no dependent pointer chasing.
+//   * BLOCK LISTS (default): every target point is stored under the eight blocks that contain its cell, so a block is
+//     ONE hash lookup and ONE contiguous run of points (grid_probe_blocks_kernel).  8x the point storage buys the removal
+//     of seven lookups and of the divergent per-cell scans.
+//   * per-cell lists (SGB_GRID_BLOCKS=0, kept for the A/B in profiles/r01): eight lookups, own cell first, the other
+//     cells pruned by their box distance (grid_probe_kernel).
+// Queries the probe cannot settle (nothing within c/2: misaligned first iterations, holes, outliers) are appended to a
+// compact pending list -- with the best candidate found so far as an upper bound -- and finished exactly:
+//   * few of them: a warp per query (pending_search_kernel): ring search over the 27 blocks at stride 2 around the query
+//     (everything within 2.5 c), then, only if that radius does not decide it, a walk of the packet tree;
+//   * many of them: the packet search (sgb_kernels_packet.cu) over the chunk-ordered queries, settled lanes idle.
+// Which of the two runs is decided on the device from the pending counter.  Results are identical to a pure tree search
+// (exact ties aside; tests/test_gpu_parity.py::test_search_structures_agree); evidence and A/B runs: profiles/r01.
 #include <cfloat>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
@@ -282,11 +287,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Few pending queries (holes, outliers, borders: a few per cent, scattered): one WARP per query walks the packet
-// records.  Every step of a single walk is a dependent load, so a thread per query would be pure latency (measured:
-// 300 us for 1000 queries); with a warp per query a leaf's points are fetched by one coalesced load and reduced by a
-// hardware min, and thousands of walks are in flight at once.  Skipped -- the packet search handles the chunk-ordered
-// queries instead -- when more than `max_pending` queries are pending.
+// Few pending queries (holes, outliers, borders: a few per mille to a few per cent, scattered): one WARP per query.
+// Ring phase first (block lists): 27 lookups in parallel, the lists scanned as one flattened run over all lanes, a
+// hardware min -- a handful of memory round trips.  Only if the ring's radius (2.5 cells) does not decide the query does
+// the warp walk the packet records: every step of a single walk is a dependent load, so a thread per query would be
+// pure latency (measured: 300 us for 1000 queries); with a warp per query a leaf's points are fetched by one coalesced
+// load and reduced by a hardware min, and thousands of walks are in flight at once.  Skipped -- the packet search handles
+// the chunk-ordered queries instead -- when more than `max_pending` queries are pending.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPendWarps = kLinBlock / 32;
 constexpr int kPendStack = 40;

@@ -1,10 +1,11 @@
 // SPDX-License-Identifier: MIT
-// Two-phase variant of linearize (profiles/r01):
-//   phase 1  nn_search_kernel      transform + exact kd-tree NN per source point, ~40 registers -> 3-4x the resident
-//                                  warps of the fused kernel (the search is latency-bound: dependent node loads)
-//   phase 2  factor_reduce_kernel  streams source + correspondences, gathers the matched target point / covariance,
-//                                  FP64 rejector + factor algebra + block reduction + last-CTA finish
-// Both phases run back to back on the context's stream; the only extra traffic is the 4-byte correspondence
+// The factor / reduction phase of linearize, and the per-thread search kept as a profiling switch (profiles/r01):
+//   nn_search_kernel      (SGB_SEARCH=1) transform + exact kd-tree NN, one query per thread -- the product path searches
+//                         with sgb_grid.cu + sgb_kernels_packet.cu instead
+//   factor_reduce_kernel  streams source + correspondences, gathers the matched target point / covariance with cp.async two
+//                         tiles ahead, FP64 rejector + factor algebra (source frame), block reduction, ticket-tree finish
+//                         and -- with several GPUs -- the exchange of the sums over the peers' mailboxes
+// Search and factor phases run back to back on the context's stream; the only extra traffic is the 4-byte correspondence
 // per point that sgb_error()/sgb_correspondences() need anyway.
 #include <cfloat>
 
