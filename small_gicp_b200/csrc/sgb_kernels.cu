@@ -199,33 +199,16 @@ __global__ void __launch_bounds__(kLinBlock) error_kernel(const __grid_constant_
     const uint32_t k = __ldg(&P.corr[i]);
     if (k == kNone) continue;
     const float4 sp = __ldg(&P.src.pts[i]);
-    const double sx = sp.x, sy = sp.y, sz = sp.z;
-    const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
-    const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
-    const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
     const float4 tq = __ldg(&P.tgt.pts[k]);
-    const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
-    double e;
-    if (FACTOR == 0) {
-      e = 0.5 * (rx * rx + ry * ry + rz * rz);
-    } else if (FACTOR == 1) {
-      const float4 n = __ldg(&P.tgt.normals[k]);
-      const double ex = static_cast<double>(n.x) * rx, ey = static_cast<double>(n.y) * ry, ez = static_cast<double>(n.z) * rz;
-      e = 0.5 * (ex * ex + ey * ey + ez * ez);
-    } else {
-      const Sym3 M = gicp_precision(P.Tlin, __ldg(&P.src.covA[i]), __ldg(&P.src.covB[i]), __ldg(&P.tgt.covA[k]), __ldg(&P.tgt.covB[k]));
-      const double mrx = M.xx * rx + M.xy * ry + M.xz * rz;
-      const double mry = M.xy * rx + M.yy * ry + M.yz * rz;
-      const double mrz = M.xz * rx + M.yz * ry + M.zz * rz;
-      e = 0.5 * (rx * mrx + ry * mry + rz * mrz);
+    float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA, t1 = sA, t2 = sA;
+    if (FACTOR == 1) t1 = __ldg(&P.tgt.normals[k]);
+    if (FACTOR == 2) {
+      sA = __ldg(&P.src.covA[i]);
+      sB = __ldg(&P.src.covB[i]);
+      t1 = __ldg(&P.tgt.covA[k]);
+      t2 = __ldg(&P.tgt.covB[k]);
     }
-    if (ROBUST == 1) {
-      const double x = sqrt(e);
-      e *= (x < P.robust_c ? 1.0 : P.robust_c / x);
-    } else if (ROBUST == 2) {
-      const double x = sqrt(e);
-      e *= P.robust_c / (P.robust_c + x * x);
-    }
+    const double e = point_error<FACTOR, ROBUST>(R, tpx, tpy, tpz, P.Tlin, P.robust_c, sp, sA, sB, tq, t1, t2);
     acc[0] += e;
   }
   block_reduce_and_finish<1, false>(acc, P.partials, P.ticket, P.out, P.comm);

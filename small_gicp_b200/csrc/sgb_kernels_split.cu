@@ -213,30 +213,12 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
     const uint32_t best = s_corr[st][tid];
     if (best != kNone) {
       const uint32_t i = tile * kLinBlock + tid;
+      // operands out of this thread's landing zone; the per-point arithmetic is point_linearize_source (sgb_math.cuh)
       const float4 sp = *slot(st, 0);
-      const double sx = sp.x, sy = sp.y, sz = sp.z;
-      const double qx = R[0] * sx + R[1] * sy + R[2] * sz + tpx;
-      const double qy = R[3] * sx + R[4] * sy + R[5] * sz + tpy;
-      const double qz = R[6] * sx + R[7] * sy + R[8] * sz + tpz;
       const float4 tq = *slot(st, F::kSrc);
-      const double rx = static_cast<double>(tq.x) - qx, ry = static_cast<double>(tq.y) - qy, rz = static_cast<double>(tq.z) - qz;
-      if (rx * rx + ry * ry + rz * rz > P.max_dist_sq_d) {  // DistanceRejector on the FP64 residual (rejector.hpp:24)
-        P.corr[i] = kNone;
-      } else {
-        // weight and residual in the SOURCE frame (D = R^T M R, rs = R^T r): see gicp_precision_source
-        Sym3 D;
-        if (FACTOR == 0) {
-          D = Sym3{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
-        } else if (FACTOR == 1) {
-          const float4 nrm = *slot(st, F::kSrc + 1);
-          D = plane_weight_source(R, nrm.x, nrm.y, nrm.z);
-        } else {
-          D = gicp_precision_source(R, *slot(st, 1), *slot(st, 2), *slot(st, F::kSrc + 1), *slot(st, F::kSrc + 2));
-        }
-        const double rsx = R[0] * rx + R[3] * ry + R[6] * rz, rsy = R[1] * rx + R[4] * ry + R[7] * rz, rsz = R[2] * rx + R[5] * ry + R[8] * rz;
-        accumulate_factor_source<ROBUST>(D, rsx, rsy, rsz, csx + sx, csy + sy, csz + sz, P.robust_c, acc);
-        acc[kAcc] += 1.0;
-      }
+      if (!point_linearize_source<FACTOR, ROBUST>(R, tpx, tpy, tpz, csx, csy, csz, P.max_dist_sq_d, P.robust_c, sp, slot(st, 1), slot(st, 2), tq,
+                                                  slot(st, F::kSrc + 1), slot(st, F::kSrc + 2), acc))
+        P.corr[i] = kNone;  // rejected: error() and sgb_correspondences() must not see it
     }
     st = st1;
   }
