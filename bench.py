@@ -397,6 +397,8 @@ def run_ours(args):
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     kern_ms = np.array([a.elapsed_time(b) for a, b in kev])
     total_ms = float(step_ms.sum())
+    # the same steps grouped by the pose of the trajectory they ran at (misaligned first iterations walk the tree, converged ones settle in the grid)
+    per_pose_ms = [float(np.mean([kern_ms[i] for i in range(args.steps) if i % len(poses) == k])) if k < args.steps else None for k in range(len(poses))]
     # ---- warm-L2 variant (what consecutive optimiser iterations actually see), informational ----
     barrier()
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -432,11 +434,29 @@ def run_ours(args):
     e2e_dev_ms = e0.elapsed_time(e1) / e2e_steps
     e2e_ms = max(e2e_wall_ms, e2e_dev_ms)
 
+    # ---- informational: one whole align() through the host-facing calls -- source uploaded ONCE from pinned host memory, then every
+    # Gauss-Newton iteration = pose in (128 B), linearize, H|b|e out (352 B) + host solve: what Registration<>::align does with the
+    # ParallelReductionCUDA glue, whose device mirror of the source is reused by all iterations of an align() ----
+    def align_e2e():
+        ctx.set_source(src_pin.numpy(), cov_pin.numpy())
+        p, _ = gn_trajectory(linearize_host)
+        return len(p)
+
+    align_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    align_reps, align_iters = 3, 0
+    for _ in range(align_reps):
+        align_iters += align_e2e()
+    torch.cuda.synchronize()
+    align_ms = (time.perf_counter() - t0) * 1e3 / align_reps
+    align_iters //= align_reps
+
     # ---- max over ranks ----
-    stats = torch.tensor([total_ms, float(kern_ms.mean()), warm_ms, e2e_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, float(kern_ms.mean()), warm_ms, e2e_ms, align_ms], dtype=torch.float64, device=dev)
     if use_dist:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms_mean, warm_ms, e2e_ms = [float(x) for x in stats.cpu()]
+    total_ms, kern_ms_mean, warm_ms, e2e_ms, align_ms = [float(x) for x in stats.cpu()]
     total_points = n_src * world
     ms_per_step = total_ms / args.steps
     value = total_points / (ms_per_step * 1e-3) / 1e6
@@ -518,6 +538,16 @@ def run_ours(args):
             },
             "cpu_baseline": cpu_baseline,
             "value_l2_warm": total_points / (warm_ms * 1e-3) / 1e6,
+            "per_pose_ms": per_pose_ms,
+            "e2e_align": {
+                "value": total_points * align_iters / (align_ms * 1e-3) / 1e6,
+                "unit": UNIT,
+                "ms_per_align": align_ms,
+                "gn_iterations": align_iters,
+                "h2d_bytes_per_align": int(n_src * 160 + 128 * align_iters),
+                "d2h_bytes_per_align": 44 * 8 * align_iters,
+                "what": "informational: whole GaussNewton align() through the host-facing calls, wall clock -- source uploaded once (pinned host, reference layout), then per iteration pose in / linearize / H|b|e out / host 6x6 solve; Mpoints/s = points x iterations / time",
+            },
             "setup": {"target_build_ms": target_build_ms, "what": "sgb_target_build_kdtree: device kd-tree construction + block lists + hash table, first call (includes allocations)"},
             "pose_error_vs_gt": {"rot_rad": rot_err, "trans_m": trans_err, "gn_iterations": len(poses)},
         }
