@@ -115,3 +115,102 @@ def test_missing_peer_times_out_instead_of_hanging(monkeypatch):
     assert np.isnan(out.cpu().numpy()[:44]).all()
     for c in ctxs:
         c.close()
+
+
+def _lm(linearize, error, max_iterations=20, max_inner=10, lam=1e-3, lam_factor=10.0):
+    """LevenbergMarquardtOptimizer::optimize (registration/optimizer.hpp:83-149) around two callbacks:
+    linearize(T) -> (H, b, e), error(T) -> e.  Returns (T, last outer index, converged)."""
+    import oracle as O
+
+    T = np.eye(4)
+    converged, it = False, 0
+    for it in range(max_iterations):
+        if converged:
+            it -= 1
+            break
+        H, b, e = linearize(T)
+        success = False
+        for _ in range(max_inner):
+            d = np.linalg.solve(H + lam * np.eye(6), -b)
+            T_new = T @ O.se3_exp(d)
+            e_new = error(T_new)
+            if e_new <= e:
+                converged = bool(np.linalg.norm(d[:3]) <= 0.1 * np.pi / 180 and np.linalg.norm(d[3:]) <= 1e-3)  # termination_criteria.hpp:10-20
+                T, e, success = T_new, e_new, True
+                lam /= lam_factor
+                break
+            lam *= lam_factor
+        if not success:
+            break
+    return T, it, converged
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_vgicp_lm_matches_unsharded_and_oracle(world):
+    """BASELINE configs[3] in miniature: Gaussian voxel map target (leaf 1.0) replicated on every rank, source sharded,
+    LevenbergMarquardt driving linearize + error through the exchange fused into the kernels.  Every rank must walk the
+    same trajectory as one context holding the whole source, and end where the CPU oracle's VGICP align ends."""
+    import torch
+
+    import oracle as O
+    from conftest import pose_error
+    from small_gicp_b200.distributed import shard_range
+
+    sg = _sg()
+    tgt, tcov, src, scov, Tgt = _pair(100_000)
+    n = src.shape[0]
+
+    def vgicp_context(lo, hi):
+        c = sg.Context(0)
+        c.build_target_voxelmap(tgt, tcov, 1.0)
+        c.set_source(src[lo:hi], scov[lo:hi])
+        return c
+
+    full = vgicp_context(0, n)
+    T_full, it_full, conv_full = _lm(lambda T: full.linearize(T, factor=sg.FACTOR_GICP), full.error)
+
+    ctxs = [vgicp_context(*shard_range(n, r, world)) for r in range(world)]
+    boxes = [c.comm_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.comm_connect_ptrs(r, world, boxes)
+    outs = [torch.zeros(64, dtype=torch.float64, device="cuda") for _ in range(world)]
+    errs = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+
+    def linearize(T):
+        for r in range(world):
+            ctxs[r].linearize_device(T, outs[r].data_ptr(), factor=sg.FACTOR_GICP)
+        for c in ctxs:
+            c.synchronize()
+        h = [o.cpu().numpy()[:44] for o in outs]
+        for r in range(1, world):
+            np.testing.assert_array_equal(h[r], h[0])  # the same sum, in the same order, on every rank
+        return h[0][:36].reshape(6, 6).copy(), h[0][36:42].copy(), float(h[0][42])
+
+    def error(T):
+        for r in reversed(range(world)):
+            ctxs[r].error_device(T, errs[r].data_ptr())
+        for c in ctxs:
+            c.synchronize()
+        e = [float(x.cpu()[0]) for x in errs]
+        assert all(x == e[0] for x in e)
+        return e[0]
+
+    T_sh, it_sh, conv_sh = _lm(linearize, error)
+    assert (it_sh, conv_sh) == (it_full, conv_full)
+    rot, trans = pose_error(T_full, T_sh)
+    assert rot < 1e-6 and trans < 1e-5, (rot, trans)  # shards re-centre their own boxes: FP32 roundings differ in the last digits
+    ninl = int(round(outs[0].cpu().numpy()[43]))
+    assert abs(ninl - full.num_inliers()) <= 3
+
+    # the CPU oracle on the same inputs: GaussianVoxelMap target, GICP factor, LM (registration_helper.cpp:130-136)
+    tc, sc = O.Cloud(tgt), O.Cloud(src)
+    tc.set_features(None, tcov)
+    sc.set_features(None, scov)
+    ref = O.Registration(factor=O.FACTOR_GICP, num_threads=max(1, O.max_threads())).align(O.GaussianVoxelMap(tc, 1.0), None, sc, np.eye(4))
+    rot, trans = pose_error(ref.T_target_source, T_sh)
+    assert rot < 1e-4 and trans < 1e-3, (rot, trans)  # BASELINE north_star bar
+    assert ref.iterations == it_sh
+    rot, trans = pose_error(Tgt, T_sh)
+    assert rot < 5e-3 and trans < 5e-2
+    for c in ctxs + [full]:
+        c.close()
