@@ -348,18 +348,10 @@ void sgb_destroy(sgb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->tgt_orig_pts, &ctx->tgt_orig_normals, &ctx->tgt_orig_covA, &ctx->tgt_orig_covB, &ctx->tgt_pts,  &ctx->tgt_normals, &ctx->tgt_covA,
-                    &ctx->tgt_covB,     &ctx->tgt_nodes,        &ctx->tgt_perm, &ctx->tgt_pnodes,     &ctx->tgt_centre,    &ctx->tgt_bounds, &ctx->vox_table, &ctx->src_pts,
-                    &ctx->src_covA,     &ctx->src_covB,         &ctx->src_perm,      &ctx->src_centre,    &ctx->src_bounds, &ctx->stage_pts, &ctx->stage_normals,
-                    &ctx->stage_covs,   &ctx->tmp_pts,          &ctx->tmp_covA,      &ctx->tmp_covB,      &ctx->keys_in,  &ctx->keys_out,    &ctx->vals_in,
-                    &ctx->pre_boxes, &ctx->grid_pending, &ctx->grid_pts, &ctx->grid_table, &ctx->grid_state, &ctx->grid_spacing, &ctx->pre_pts, &ctx->pre_leaf_pts, &ctx->pre_nodes, &ctx->pre_perm, &ctx->pre_centre, &ctx->pre_bounds, &ctx->pre_out_normals, &ctx->pre_out_covs, &ctx->pre_heads, &ctx->pre_slots, &ctx->pre_vals_out,
-                    &ctx->sort_temp,    &ctx->corr,             &ctx->partials,      &ctx->ticket,        &ctx->out44,    &ctx->corr64};
-  for (DevBuf* b : bufs) b->release();
-  sgb_comm_disconnect(ctx);
-  ctx->comm_mail.release();
+  sgb_comm_disconnect(ctx);  // unmaps the peers' mailboxes
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  delete ctx;
+  delete ctx;  // every DevBuf member frees its allocation (the context's device is current)
 }
 
 const char* sgb_last_error(const sgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -463,7 +455,12 @@ int sgb_comm_connect(sgb_ctx* ctx, int rank, int world, const void* handles) {
     }
     opened[p] = true;
   }
-  if (int rc = sgb_comm_connect_ptrs(ctx, rank, world, ptrs)) return rc;
+  if (int rc = sgb_comm_connect_ptrs(ctx, rank, world, ptrs)) {
+    for (int p = 0; p < world; p++)
+      if (opened[p]) cudaIpcCloseMemHandle(ptrs[p]);
+    sgb_comm_disconnect(ctx);  // forget the (now unmapped) pointers
+    return rc;
+  }
   for (int p = 0; p < world; p++) ctx->comm_ipc_opened[p] = opened[p];
   return 0;
 }

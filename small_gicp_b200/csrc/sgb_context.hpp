@@ -9,9 +9,14 @@
 namespace sgb {
 
 /// Grow-only device buffer (re-used across calls so that streams of similarly sized frames never reallocate).
+/// Owns its allocation: freed with the context (sgb_destroy makes the context's device current first).
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
@@ -101,7 +106,7 @@ struct sgb_ctx {
   bool corr_seeds = false;  // corr[] holds correspondences of the current (target, tree, source) triple
   int lin_factor = 0, lin_robust = 0;
   double lin_c = 1.0;
-  double Tlin[12];
+  double Tlin[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   const double* last_out = nullptr;  // device pointer holding H|b|e|inliers of the last linearize
   int lin_grid = 0;
 };
