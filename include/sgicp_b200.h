@@ -10,7 +10,12 @@
  * returns a description.  There is NO CPU fallback: without a CUDA device sgb_create() fails.
  *
  * All host input buffers are borrowed for the duration of the call only; the context owns all
- * device memory.  Host layouts are exactly the reference's in-memory layouts so that the header
+ * device memory.  One exception, by CUDA's own rules: a cloud passed in PAGE-LOCKED host memory
+ * (cudaMallocHost / cudaHostRegister / torch pin_memory) is copied asynchronously on the context's
+ * stream, so sgb_{target,source}_set_points / sgb_target_set_voxelmap may return before it has been
+ * read -- leave such a buffer unchanged until sgb_synchronize() or any call that returns results to
+ * the host (sgb_linearize, sgb_error, sgb_correspondences, ...).  Pageable memory (std::vector,
+ * numpy) is consumed when the call returns.  Host layouts are exactly the reference's in-memory layouts so that the header
  * glue can pass `cloud.points[0].data()` etc. without repacking:
  *   points / normals : N x 4 doubles (x,y,z,1) / (nx,ny,nz,0)   -- std::vector<Eigen::Vector4d>,
  *                      include/small_gicp/points/point_cloud.hpp:69-70
