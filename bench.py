@@ -141,6 +141,18 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout_s):
+        """block until nvidia-smi has written its first line (it needs ~0.1 s to start)"""
+        t0 = time.perf_counter()
+        while self.proc and time.perf_counter() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.02)
+        return False
+
     def stop(self):
         res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
@@ -375,9 +387,24 @@ def run_ours(args):
         flush.zero_()
         step_device(poses[i % len(poses)])
     barrier()
+    # Clocks: nvidia-smi needs ~0.1 s to start and samples every 0.1 s, the K timed steps take ~10 ms.  The sampler therefore runs
+    # over the timed steps PLUS the same step repeated untimed before and after them (identical load, ~0.5 s each side), so that
+    # the reported clocks / throttle reasons are those of the GPU under exactly this load.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample(1.5)
+    roll_steps = int(min(2000, max(20, 2_000_000_000 // max(1, n_src))))  # the same count on every rank (the step holds a collective)
+
+    def load_roll():
+        for i in range(roll_steps):
+            flush.zero_()
+            step_device(poses[i % len(poses)])
+            if i % 64 == 63:
+                stream.synchronize()  # keep the launch queue short
+        barrier()
+
+    load_roll()
     launches0 = ctx.kernel_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -408,7 +435,10 @@ def run_ours(args):
     w1.record(stream)
     barrier()
     warm_ms = w0.elapsed_time(w1) / args.steps
+    load_roll()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = f"the {args.steps} timed steps + {roll_steps} identical untimed steps before and after them"
 
     # ---- e2e: host buffers through the C-ABI, H2D of the step's inputs + D2H of H|b|e inside the timed region ----
     h_out = torch.zeros(64, dtype=torch.float64).pin_memory()

@@ -109,12 +109,13 @@ int build_grid(sgb_ctx* ctx) {
   CU(ctx->vals_in.reserve(n_ent * sizeof(uint32_t)));
   CU(ctx->pre_vals_out.reserve(n_ent * sizeof(uint32_t)));
   CU(ctx->grid_pts.reserve(n_ent * sizeof(float4)));
-  CU(ctx->grid_pending.reserve(sizeof(uint32_t)));
+  CU(ctx->grid_pending.reserve(2 * sizeof(uint32_t)));
   size_t tb = 0;
   CU(sort_pairs_u64_u32(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), n_ent,
                         ctx->stream));
   CU(ctx->sort_temp.reserve(tb));
-  uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the pending counter doubles as scratch during construction
+  uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the two pending counters double as scratch during construction
+  uint32_t* d_max_list = d_distinct + 1;
   CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, blocks, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
                       ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->stream));
   uint32_t distinct = 0;
@@ -124,10 +125,15 @@ int build_grid(sgb_ctx* ctx) {
   while (capacity < 2ull * distinct) capacity <<= 1;  // load factor <= 1/2
   CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
   CU(launch_grid_fill(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n_ent),
-                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->stream));
+                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, d_max_list, ctx->stream));
   ctx->grid_blocks = blocks;
-  ctx->pending_clean = false;  // d_distinct lives in the first pending counter
+  ctx->pending_clean = false;  // d_distinct / d_max_list live in the pending counters
   ctx->launches += 9;
+  uint32_t max_list = 0;
+  CU(cudaMemcpyAsync(&max_list, d_max_list, sizeof(max_list), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->debug_pending) std::fprintf(stderr, "[sgb] grid front end: cell %.4g, %u distinct lists, longest %u points\n", cell, distinct, max_list);
+  if (max_list > kGridMaxList) return 0;  // degenerate density (see kGridMaxList): the tree search alone stays exact and bounded
   for (int a = 0; a < 3; a++) ctx->grid_origin[a] = g.origin[a];
   ctx->grid_inv_cell = g.inv_cell;
   ctx->grid_settle_d2 = g.settle_d2;

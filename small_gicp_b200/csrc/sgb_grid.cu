@@ -70,7 +70,7 @@ __global__ void grid_count_heads_kernel(const uint64_t* __restrict__ keys, uint3
 
 // after the sort: gather the points into cell order (w = leaf position) and insert one table entry per run of equal keys
 __global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ leaf_pos, const float4* __restrict__ leaf_pts, uint32_t n,
-                                 float4* grid_pts, GridSlot* table, uint32_t mask) {
+                                 float4* grid_pts, GridSlot* table, uint32_t mask, uint32_t* max_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t lp = leaf_pos[i];
@@ -88,6 +88,7 @@ __global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32
     }
     table[slot].start = i;
     table[slot].count = cnt;
+    atomicMax(max_count, cnt);  // longest list: build_grid drops the front end when one query would have to scan thousands of points
   }
 }
 
@@ -516,9 +517,11 @@ cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParam
 }
 
 cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
-                             uint32_t capacity, cudaStream_t st) {
+                             uint32_t capacity, uint32_t* d_max_count, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d_max_count, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
   grid_table_init_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
-  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u);
+  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u, d_max_count);
   return cudaGetLastError();
 }
 

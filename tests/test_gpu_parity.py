@@ -406,6 +406,56 @@ def test_grid_far_and_unbounded_queries(synthetic_pair, monkeypatch):
     assert out["tree"][1][3] == len(sc)  # no rejector: every source point keeps a correspondence, however far
 
 
+def test_degenerate_density_stays_exact_and_bounded():
+    """Inputs the grid front end must not choke on (kdtree_synthetic_test.cpp:26-93 spirit: clusters, duplicates, huge range):
+    half of the target in a 1 cm cluster (a block list of thousands of points: the front end is dropped, kGridMaxList), exact
+    duplicates, and two outliers at +-1e5 m that stretch the box (the cell-count bound inflates the cell).  The search must stay
+    exact -- brute force on a sample, ICP sums vs numpy -- and finish promptly."""
+    import time
+
+    from scipy.spatial import cKDTree
+
+    import np_factors as NF
+
+    sg = _sg()
+    rng = np.random.default_rng(11)
+    plane = np.c_[rng.uniform(-50, 50, (20_000, 2)), rng.normal(0, 0.01, 20_000)]
+    cluster = np.array([3.0, -2.0, 0.5]) + rng.uniform(-0.005, 0.005, (20_000, 3))
+    dup = np.repeat(plane[:500], 4, axis=0)
+    for extra in (np.zeros((0, 3)), np.array([[1e5, 0.0, 0.0], [-1e5, 2e4, 0.0]])):
+        tgt = np.concatenate([plane, cluster, dup, extra]).astype(np.float32).astype(np.float64)
+        src = np.concatenate([plane[::2] + rng.normal(0, 0.02, (10_000, 3)), cluster[::4] + rng.normal(0, 0.002, (5_000, 3)), [[40.0, 40.0, 30.0]]])
+        src = src.astype(np.float32).astype(np.float64)
+        ctx = sg.Context(0)
+        ctx.set_target(tgt)
+        ctx.build_target_kdtree(0)
+        ctx.set_source(src)
+        t0 = time.perf_counter()
+        T = np.eye(4)
+        T[:3, 3] = [0.03, -0.02, 0.01]
+        H, b, e = ctx.linearize(T, factor=sg.FACTOR_ICP, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0)
+        dt = time.perf_counter() - t0
+        assert dt < 2.0, dt  # a per-thread scan of a 20k-point list per query would take far longer
+        corr = ctx.correspondences()
+        q = src @ T[:3, :3].T + T[:3, 3]
+        d, j = cKDTree(tgt).query(q)
+        got = np.where(corr == NF.NO, np.inf, np.linalg.norm(tgt[np.minimum(corr, len(tgt) - 1).astype(np.int64)] - q, axis=1))
+        want = np.where(d * d > 1.0, np.inf, d)
+        clear = np.abs(d * d - 1.0) > 1e-4
+        # same nearest DISTANCE (duplicates / near-ties may pick another index); FP32 search on coordinates centred on a box that the
+        # outliers stretch to 2e5 m carries ~8 mm of rounding, on the un-stretched box ~4 um
+        tol = 2e-2 if len(extra) else 1e-4
+        fin = np.isfinite(want) & np.isfinite(got) & clear
+        assert np.all(np.isfinite(want[clear]) == np.isfinite(got[clear]))
+        assert np.all(np.abs(got[fin] - want[fin]) <= tol), float(np.abs(got[fin] - want[fin]).max())
+        p4 = lambda a: np.c_[a, np.ones(len(a))]
+        H2, b2, e2 = NF.linearize(T, corr, sg.FACTOR_ICP, 0, 1.0, p4(src), None, p4(tgt), None, None)
+        assert np.linalg.norm(H - H2) <= (1e-3 if len(extra) else 2e-5) * np.linalg.norm(H2)
+        assert abs(e - e2) <= (2e-2 if len(extra) else 2e-5) * e2
+        assert corr[-1] == NF.NO  # 30 m above everything: rejected
+        ctx.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 full size (1M x 1M): size-independent properties instead of an oracle run.
       * own-tree NN == brute-force NN on a random sample of queries (exactness)
