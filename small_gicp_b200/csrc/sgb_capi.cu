@@ -211,7 +211,17 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
         settled = ctx->grid_state.as<uint8_t>();
         pending_count = pc;
       }
-      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, ctx->stream));
+      uint32_t *queue = nullptr, *queue_next = nullptr;
+      if (ctx->use_packet_queue) {
+        if (!ctx->packet_queue.p) {  // first use: two zeroed counters (afterwards every launch clears the other one)
+          CU(ctx->packet_queue.reserve(2 * sizeof(uint32_t)));
+          CU(cudaMemsetAsync(ctx->packet_queue.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+        }
+        queue = ctx->packet_queue.as<uint32_t>() + ctx->packet_parity;
+        queue_next = ctx->packet_queue.as<uint32_t>() + (ctx->packet_parity ^ 1);
+        ctx->packet_parity ^= 1;
+      }
+      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, ctx->stream));
       if (ctx->debug_pending && pending_count) {  // profiling aid: synchronises
         uint32_t h = 0;
         CU(cudaMemcpyAsync(&h, pending_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -333,6 +343,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
     const double v = atof(s);
     if (v > 0.1 && v < 100.0) ctx->grid_cell_factor = v;
   }
+  if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
   ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
   if (const char* s = getenv("SGB_COMM_TIMEOUT_MS")) ctx->comm_timeout_ns = static_cast<unsigned long long>(std::max(1, atoi(s))) * 1000000ull;
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement

@@ -71,6 +71,9 @@ struct sgb_ctx {
   uint32_t grid_capacity = 0;
   bool pending_clean = false;  // both pending counters are zero / maintained by the probe kernels
   int pending_parity = 0;
+  sgb::DevBuf packet_queue;      // two alternating chunk-queue counters of the packet search (each launch clears the other)
+  int packet_parity = 0;
+  bool use_packet_queue = true;  // profiling switch SGB_PACKET_QUEUE=0: static stride
   float grid_origin[3] = {0, 0, 0}, grid_inv_cell = 1.f, grid_settle_d2 = 0.f, grid_cell = 0.f;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;

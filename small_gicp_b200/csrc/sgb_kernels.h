@@ -55,8 +55,9 @@ cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t*
 
 // sgb_kernels_packet.cu
 int packet_occupancy(int max_depth);
+/// queue / queue_next: two alternating zero-initialised counters of the dynamic chunk queue (this launch clears queue_next), or null = static stride
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
-                                 uint32_t min_pending, cudaStream_t st);
+                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, cudaStream_t st);
 // sgb_grid.cu: uniform-grid front end of the search
 struct GridParams {
   float origin[3];  // minimum corner of the target's box (centred frame)

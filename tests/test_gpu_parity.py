@@ -337,7 +337,7 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     tc, tt, sc, Tgt, nt = synthetic_pair
     sg = _sg()
     results = {}
-    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL")
+    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE")
     for name, env, own in (
         ("device-kd/grid", {}, True),
         ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
@@ -345,6 +345,8 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
         ("device-kd/grid-no-ring", {"SGB_RING": "0"}, True),
         ("device-kd/grid-warp-per-pending", {"SGB_PENDING_DIV": "1"}, True),
         ("device-kd/grid-packet-pending", {"SGB_PENDING_DIV": "1000000"}, True),
+        ("device-kd/grid-packet-pending-static-stride", {"SGB_PENDING_DIV": "1000000", "SGB_PACKET_QUEUE": "0"}, True),
+        ("device-kd/no-grid-static-stride", {"SGB_GRID": "0", "SGB_PACKET_QUEUE": "0"}, True),
         ("device-kd/grid-small-cells", {"SGB_GRID_CELL": "0.7"}, True),
         ("device-kd/grid-small-cells-warp", {"SGB_GRID_CELL": "0.7", "SGB_PENDING_DIV": "1"}, True),
         ("device-kd/grid-large-cells", {"SGB_GRID_CELL": "6"}, True),
