@@ -13,7 +13,6 @@
 // children (64 B, "BVH2" layout):  float4[4] = {L.lo|L.a, L.hi|L.b, R.lo|R.a, R.hi|R.b} where a child is a leaf
 // (a = first point, b = count > 0) or an inner node (a = node index, b = 0).
 #include <cfloat>
-#include <cstdlib>
 
 #include "sgb_device.cuh"
 #include "sgb_kernels.h"
@@ -32,13 +31,9 @@ __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const f
   return dx * dx + dy * dy + dz * dz;
 }
 
-/// MIN_CTAS: resident CTAs per SM the register allocation is held to (launch bound).  12 = what 40 registers give by themselves;
-/// 16 (32 registers) trades a few spilled loop invariants for more walks in flight -- the kernel's time is the dependent-load chain of a
-/// walk times the walks per warp (profiles/r01/ai), so residency is worth more than registers.  A/B switch SGB_PACKET_CTAS.
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
+__global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
                                                                   const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
-                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, int prefetch_far) {
+                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next) {
   // Work distribution: chunks (32 consecutive queries) differ wildly in cost -- all lanes settled by the grid probe, or 32
   // tree walks through a misaligned wall -- and a static stride left a third of the warps idle for the second half of the
   // kernel (profiles/r01/ai: 39-52 % achieved occupancy of 75 %).  With `queue` the warps take their first chunk by rank and
@@ -118,15 +113,8 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
           const unsigned closer_l = __ballot_sync(0xffffffffu, (wl || wr) && dl <= dr);
           const bool left_first = 2 * __popc(closer_l) >= __popc(ml | mr);
           my_dist[sp * kLinBlock] = left_first ? dr : dl;
-          const uint2 far_child = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
-          if (lane == 0) my_child[sp] = far_child;
+          if (lane == 0) my_child[sp] = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
           sp++;
-          if (prefetch_far) {
-            // the far child is usually popped a few steps later: have its record (inner) / its points (leaf, one 128 B line per
-            // lane) on their way to L2 by then instead of paying the miss on the walk's dependent chain
-            const char* a = far_child.y == 0u ? reinterpret_cast<const char*>(pnodes + far_child.x * 4u) : reinterpret_cast<const char*>(pts + far_child.x) + lane * 128u;
-            if (far_child.y == 0u ? lane == 0u : lane * 8u < far_child.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-          }
           ca = left_first ? __float_as_uint(n0.w) : __float_as_uint(n2.w);
           cb = left_first ? __float_as_uint(n1.w) : __float_as_uint(n3.w);
           leaf_d = left_first ? dl : dr;
@@ -223,24 +211,10 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
   }
 }
 
-using PacketKernel = void (*)(LinParams, const float4*, int, const uint8_t*, const uint32_t*, uint32_t, uint32_t*, uint32_t*, int);
-static int packet_ctas() {
-  static const int v = std::getenv("SGB_PACKET_CTAS") ? std::atoi(std::getenv("SGB_PACKET_CTAS")) : 12;  // profiling switch
-  return v;
-}
-static int packet_prefetch() {
-  static const int v = std::getenv("SGB_PACKET_PREFETCH") ? std::atoi(std::getenv("SGB_PACKET_PREFETCH")) : 0;  // profiling switch
-  return v;
-}
-static PacketKernel packet_kernel() {
-  const int c = packet_ctas();
-  return c >= 16 ? packet_search_kernel<16> : packet_search_kernel<12>;
-}
-
 int packet_occupancy(int max_depth) {
   int nb = 0;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_kernel(), kLinBlock, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel, kLinBlock, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
@@ -249,10 +223,10 @@ cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int g
   if (max_depth > 40) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
   if (!settled) {  // no grid front end: nothing on the stream this launch could overlap with
-    packet_kernel()<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, packet_prefetch());
+    packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next);
     return cudaGetLastError();
   }
-  return launch_dependent(packet_kernel(), grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, packet_prefetch());
+  return launch_dependent(packet_search_kernel, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next);
 }
 
 }  // namespace sgb
