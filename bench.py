@@ -395,6 +395,8 @@ def run_ours(args):
         sampler.start()
         sampler.wait_first_sample(1.5)
     roll_steps = int(min(2000, max(20, 2_000_000_000 // max(1, n_src))))  # the same count on every rank (the step holds a collective)
+    if os.environ.get("SGB_BENCH_ROLL"):  # profiler runs: a short roll keeps the launch numbering simple (ncu -s / -c)
+        roll_steps = max(1, int(os.environ["SGB_BENCH_ROLL"]))
 
     def load_roll():
         for i in range(roll_steps):
