@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn one `scripts/gpu_round.sh` visit (gpurun_out/<tag>/) into the tracked artefacts under profiles/:
+"""Turn one `scripts/gpu_ncu.sh` (or `gpu_round.sh`) visit (gpurun_out/<tag>/) into the tracked artefacts under profiles/:
    profiles/<round>/<letter>_linearize.md  -- per-kernel ncu summary of the four launches of sgb_linearize over the bench's poses
    profiles/linearize_traffic.json         -- mean DRAM bytes per linearize (feeds bench.py's roofline.traffic)
    copies of the bench lines and launch lists.
@@ -52,7 +52,7 @@ def main():
     r = json.load(open(os.path.join(src, "bench_ref.json")))
     L = []
     L.append(f"# {os.path.basename(dst)}/{tag} -- the four launches of `sgb_linearize` (1M x 1M synthetic GICP), ncu --set full\n")
-    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|pending_search|packet_search|factor_reduce" -s 40 -c 20 python bench.py --steps 20 --warmup 3 --no-cpu-baseline`')
+    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|pending_search|packet_search|factor_reduce" -s 32 -c 20 python bench.py --steps 20 --warmup 3 --no-cpu-baseline` with `SGB_BENCH_ROLL=5` (`scripts/gpu_ncu.sh`)')
     L.append(f"(k=20 covariances, L2 flushed between steps; the captured launches are one pass over the {len(groups)} poses of the Gauss-Newton trajectory: {len(conv)} converged, {len(mis)} misaligned).")
     L.append("Which search kernel does the work is decided on the device from the probe's pending counter; the other one exits at once.\n")
     L.append(f"## Converged poses -- mean of {len(conv)} linearizes\n")
