@@ -201,7 +201,7 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
         uint32_t* pbase = ctx->grid_pending.as<uint32_t>();
         uint32_t* pc = pbase + ctx->pending_parity;
         uint32_t* plist = pbase + 2;
-        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->grid_state.as<uint8_t>(), pc,
+        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->probe_batch_tail, ctx->grid_state.as<uint8_t>(), pc,
                              plist, pbase + (ctx->pending_parity ^ 1), ctx->stream));
         ctx->pending_parity ^= 1;
         CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, plist, pending_split, ctx->grid_pts.as<float4>(),
@@ -343,6 +343,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
     const double v = atof(s);
     if (v > 0.1 && v < 100.0) ctx->grid_cell_factor = v;
   }
+  if (const char* s = getenv("SGB_PROBE_TAIL")) ctx->probe_batch_tail = (s[0] == '1');        // 1 = probe scans its list in clamped batches of eight (A/B, sgb_grid.cu)
   if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
   ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
   if (const char* s = getenv("SGB_COMM_TIMEOUT_MS")) ctx->comm_timeout_ns = static_cast<unsigned long long>(std::max(1, atoi(s))) * 1000000ull;

@@ -217,7 +217,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
 // ---------------------------------------------------------------------------------------------------------------
-template <int MIN_CTAS>
+// BATCH_TAIL (A/B switch SGB_PROBE_TAIL=1, off by default until measured): the plain loop below is unrolled by 8, which leaves a
+// remainder loop of count % 8 iterations with ONE load in flight each -- 15 % of the kernel's stall samples sit on that
+// load's first use (profiles/r01/am).  The batched form always issues eight loads, clamping the index to the last point of
+// the list: a repeated point can never be strictly closer than itself, so the result is unchanged.
+template <int MIN_CTAS, bool BATCH_TAIL>
 __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
                                                                uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
@@ -251,14 +255,32 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
     for (uint32_t off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + off));
     if (bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + bytes - 16u));  // last line of a run that is not 128 B aligned
     const float4* __restrict__ cp = grid_pts + e.x;
+    if (BATCH_TAIL) {
+      const uint32_t last = e.y - 1u;  // only used when e.y > 0
+      for (uint32_t base = 0; base < e.y; base += 8u) {
+        float4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldg(&cp[min(base + static_cast<uint32_t>(u), last)]);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const float dx = t[u].x - fx, dy = t[u].y - fy, dz = t[u].z - fz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = __float_as_uint(t[u].w);
+          }
+        }
+      }
+    } else {
 #pragma unroll 8
-    for (uint32_t j = 0; j < e.y; j++) {
-      const float4 t = __ldg(&cp[j]);
-      const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-      const float d = dx * dx + dy * dy + dz * dz;
-      if (d < best_d) {
-        best_d = d;
-        best = __float_as_uint(t.w);
+      for (uint32_t j = 0; j < e.y; j++) {
+        const float4 t = __ldg(&cp[j]);
+        const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best_d) {
+          best_d = d;
+          best = __float_as_uint(t.w);
+        }
       }
     }
   }
@@ -526,19 +548,21 @@ cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_s
 }
 
 cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st) {
+                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st) {
   // *pending_count must be zero on entry: the previous probe (or the context) cleared it
   const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
   if (blocks)
   {
     static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;  // profiling switch
-    if (ctas == 6)
-      grid_probe_blocks_kernel<6><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    if (batch_tail)
+      grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    else if (ctas == 6)
+      grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
     else if (ctas == 8)
-      grid_probe_blocks_kernel<8><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+      grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
     else
-      grid_probe_blocks_kernel<5><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+      grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
   }
   else
     grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, next_count);

@@ -77,7 +77,7 @@ cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_s
 /// points, or a few far outliers stretching the box so that the cell-count bound inflates the cell) and the exact tree search alone is used
 constexpr uint32_t kGridMaxList = 2048;
 cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st);
+                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st);
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
                                   uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
                                   cudaStream_t st);

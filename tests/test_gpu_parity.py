@@ -337,7 +337,7 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     tc, tt, sc, Tgt, nt = synthetic_pair
     sg = _sg()
     results = {}
-    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE")
+    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_PROBE_TAIL")
     for name, env, own in (
         ("device-kd/grid", {}, True),
         ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
@@ -350,6 +350,7 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
         ("device-kd/grid-small-cells", {"SGB_GRID_CELL": "0.7"}, True),
         ("device-kd/grid-small-cells-warp", {"SGB_GRID_CELL": "0.7", "SGB_PENDING_DIV": "1"}, True),
         ("device-kd/grid-large-cells", {"SGB_GRID_CELL": "6"}, True),
+        ("device-kd/grid-batched-tail", {"SGB_PROBE_TAIL": "1"}, True),
         ("device-lbvh/grid", {"SGB_TREE": "lbvh"}, True),
         ("host-kd/packet", {"SGB_TREE": "host"}, True),
         ("reference-kd/packet", {}, False),
