@@ -74,7 +74,7 @@ struct sgb_ctx {
   sgb::DevBuf packet_queue;      // two alternating chunk-queue counters of the packet search (each launch clears the other)
   int packet_parity = 0;
   bool use_packet_queue = true;  // profiling switch SGB_PACKET_QUEUE=0: static stride
-  bool probe_batch_tail = false; // A/B switch SGB_PROBE_TAIL=1: block-list scan in clamped batches of eight (not yet measured)
+  bool probe_batch_tail = false; // A/B switch SGB_PROBE_TAIL=1: block-list scan in clamped batches of eight (measured: no gain)
   float grid_origin[3] = {0, 0, 0}, grid_inv_cell = 1.f, grid_settle_d2 = 0.f, grid_cell = 0.f;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;

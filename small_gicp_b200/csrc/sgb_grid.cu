@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
 // ---------------------------------------------------------------------------------------------------------------
-// BATCH_TAIL (A/B switch SGB_PROBE_TAIL=1, off by default until measured): the plain loop below is unrolled by 8, which leaves a
+// BATCH_TAIL (A/B switch SGB_PROBE_TAIL=1; measured once at the end of round 1: no gain, stays off -- profiles/r01/am_linearize.md): the plain loop below is unrolled by 8, which leaves a
 // remainder loop of count % 8 iterations with ONE load in flight each -- 15 % of the kernel's stall samples sit on that
 // load's first use (profiles/r01/am).  The batched form always issues eight loads, clamping the index to the last point of
 // the list: a repeated point can never be strictly closer than itself, so the result is unchanged.
