@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <utility>
 
+#include "read_points.hpp"
 #include "core.hpp"
 #include "factors.hpp"
 #include "kdtree.hpp"
@@ -156,6 +157,18 @@ inline RegistrationResult align(const PointCloud& target_raw, const PointCloud& 
     return align(*voxelmap, *source, init_T, setting);
   }
   return align(*target, *source, *target_tree, init_T, setting);
+}
+
+/// Raw single-precision points (registration_helper.hpp:26-29: the std::vector<Eigen::Vector4f> overload).
+inline std::pair<PointCloud::Ptr, std::shared_ptr<KdTree<PointCloud>>> preprocess_points(const std::vector<Vector4f>& points, double downsampling_resolution,
+                                                                                         int num_neighbors = 10, int num_threads = 4, int device = 0) {
+  return preprocess_points(*make_point_cloud(points), downsampling_resolution, num_neighbors, num_threads, device);
+}
+
+/// Raw single-precision points in, registration out (registration_helper.hpp:57-63, registration_helper.cpp:37-56).
+inline RegistrationResult align(const std::vector<Vector4f>& target, const std::vector<Vector4f>& source, const Isometry3d& init_T = Isometry3d::Identity(),
+                                const RegistrationSetting& setting = RegistrationSetting()) {
+  return align(*make_point_cloud(target), *make_point_cloud(source), init_T, setting);
 }
 
 }  // namespace small_gicp_b200

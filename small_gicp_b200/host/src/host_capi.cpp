@@ -236,4 +236,32 @@ int sgbh_kdtree_knn(size_t n, const double* pts4, size_t nq, const double* queri
   }
 }
 
+/// read_ply / read_points of the host mirror (read_points.hpp): fills at most `capacity` points (x, y, z, 1 as floats), returns the
+/// number of points in the file through n_out (API-surface check of the mirror, CPU-only).  kind: 0 = PLY, 1 = KITTI .bin.
+int sgbh_read_points(const char* filename, int kind, size_t capacity, float* out_xyz1, size_t* n_out) {
+  try {
+    const std::vector<Vector4f> pts = kind == 0 ? read_ply(filename) : read_points(filename);
+    *n_out = pts.size();
+    const size_t m = pts.size() < capacity ? pts.size() : capacity;
+    if (m) std::memcpy(out_xyz1, pts.data(), m * sizeof(Vector4f));
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 2;
+  }
+}
+
+/// write_points of the host mirror.
+int sgbh_write_points(const char* filename, size_t n, const float* xyz1) {
+  try {
+    std::vector<Vector4f> pts(n);
+    if (n) std::memcpy(pts.data(), xyz1, n * sizeof(Vector4f));
+    write_points(filename, pts);
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 2;
+  }
+}
+
 }  // extern "C"

@@ -134,3 +134,29 @@ def kdtree_knn(points, queries, k):
     if rc != 0:
         raise capi.SgbError(L.sgbh_last_error().decode())
     return idx, d2
+
+
+def read_points_cpp(filename, kind="ply"):
+    """read_ply / read_points of the C++ host mirror (small_gicp_b200/host/include/small_gicp_b200/read_points.hpp) -> (N, 4) float32."""
+    L = _lib()
+    n = C.c_size_t(0)
+    k = 0 if kind == "ply" else 1
+    fn = str(filename).encode()
+    L.sgbh_read_points.restype = C.c_int
+    L.sgbh_read_points.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+    if L.sgbh_read_points(fn, k, 0, None, C.byref(n)) != 0:
+        raise capi.SgbError(L.sgbh_last_error().decode())
+    out = np.empty((n.value, 4), dtype=np.float32)
+    if n.value and L.sgbh_read_points(fn, k, n.value, out.ctypes.data_as(C.c_void_p), C.byref(n)) != 0:
+        raise capi.SgbError(L.sgbh_last_error().decode())
+    return out
+
+
+def write_points_cpp(filename, points):
+    """write_points of the C++ host mirror: (N, 4) float32 -> KITTI-style .bin"""
+    L = _lib()
+    p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 4)
+    L.sgbh_write_points.restype = C.c_int
+    L.sgbh_write_points.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    if L.sgbh_write_points(str(filename).encode(), p.shape[0], p.ctypes.data_as(C.c_void_p)) != 0:
+        raise capi.SgbError(L.sgbh_last_error().decode())
