@@ -394,6 +394,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         sampler.wait_first_sample(1.5)
+    barrier()  # rank 0 waited for the sampler: every rank enters the first collective step of the roll together
     roll_steps = int(min(2000, max(20, 2_000_000_000 // max(1, n_src))))  # the same count on every rank (the step holds a collective)
     if os.environ.get("SGB_BENCH_ROLL"):  # profiler runs: a short roll keeps the launch numbering simple (ncu -s / -c)
         roll_steps = max(1, int(os.environ["SGB_BENCH_ROLL"]))
