@@ -1,18 +1,17 @@
 // SPDX-License-Identifier: MIT
-// On-disk readers of the reference's benchmark / example inputs, for the Eigen-free host mirror
-// (/root/reference/include/small_gicp/benchmark/read_points.hpp):
-//   read_points  : KITTI velodyne .bin = N x (x, y, z, intensity) float32; w is overwritten with 1   (:15-33)
-//   write_points : the inverse                                                                       (:38-46)
-//   read_ply     : binary PLY whose vertex properties are all `float`, the first three named x y z   (:52-109)
-// Same behaviour on bad input as the reference: a message on std::cerr and an empty result, never an exception.
-// One deliberate difference: read_ply reads `#properties x #vertices` floats; the reference reads `4 x #vertices`
-// (read_points.hpp:100-101), which is the same thing for its bundled files (x, y, z, intensity) and a short read otherwise.
+// File readers for the inputs the reference's examples and benchmarks use, for the Eigen-free host mirror.  Behavioural model:
+// /root/reference/include/small_gicp/benchmark/read_points.hpp
+//   read_points  (:15-33)   KITTI velodyne .bin -- packed float32 records (x, y, z, intensity); the fourth value is replaced by 1
+//   write_points (:38-46)   the same records back to disk
+//   read_ply     (:52-109)  binary PLY whose vertex properties are all `float`, x y z first
+// Like the reference, bad input never throws: one line on stderr, empty result.  One deliberate difference: read_ply consumes
+// (#properties x #vertices) floats, where the reference always reads 4 x #vertices (:100-101) -- identical for its bundled
+// x/y/z/intensity files, a short read for any other property count.
 #pragma once
 #include <array>
-#include <cctype>
-#include <fstream>
-#include <iostream>
-#include <sstream>
+#include <cstdio>
+#include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -24,94 +23,118 @@ namespace small_gicp_b200 {
 using Vector4f = std::array<float, 4>;
 static_assert(sizeof(Vector4f) == 16, "Vector4f must be four packed floats");
 
-inline std::vector<Vector4f> read_points(const std::string& filename) {
-  std::ifstream ifs(filename, std::ios::binary | std::ios::ate);
-  if (!ifs) {
-    std::cerr << "error: failed to open " << filename << std::endl;
-    return {};
+namespace detail {
+
+struct FileCloser {
+  void operator()(std::FILE* f) const {
+    if (f) std::fclose(f);
   }
-  const std::streamsize bytes = ifs.tellg();
-  const size_t n = bytes > 0 ? static_cast<size_t>(bytes) / sizeof(Vector4f) : 0;
-  ifs.seekg(0, std::ios::beg);
-  std::vector<Vector4f> points(n);
-  ifs.read(reinterpret_cast<char*>(points.data()), static_cast<std::streamsize>(sizeof(Vector4f) * n));
-  for (auto& p : points) p[3] = 1.0f;
-  return points;
+};
+using File = std::unique_ptr<std::FILE, FileCloser>;
+
+inline File open_file(const std::string& path, const char* mode) {
+  File f(std::fopen(path.c_str(), mode));
+  if (!f) std::fprintf(stderr, "error: failed to open %s\n", path.c_str());
+  return f;
 }
 
-inline void write_points(const std::string& filename, const std::vector<Vector4f>& points) {
-  std::ofstream ofs(filename, std::ios::binary);
-  if (!ofs) {
-    std::cerr << "error: failed to open " << filename << std::endl;
-    return;
-  }
-  ofs.write(reinterpret_cast<const char*>(points.data()), static_cast<std::streamsize>(sizeof(Vector4f) * points.size()));
-}
+/// What a PLY header tells us: vertex count, number of float properties per vertex, and whether it is usable here.
+struct PlyHeader {
+  size_t vertices = 0;
+  size_t floats_per_vertex = 0;
+  bool ok = false;
+};
 
-inline std::vector<Vector4f> read_ply(const std::string& filename) {
-  std::ifstream ifs(filename, std::ios::binary);
-  if (!ifs) {
-    std::cerr << "error: failed to open " << filename << std::endl;
-    return {};
-  }
-  std::vector<std::string> properties;
-  size_t n = 0;
-  bool header_done = false;
-  std::string line;
-  while (std::getline(ifs, line)) {
-    if (!line.empty() && line.back() == '\r') line.pop_back();
+inline PlyHeader parse_ply_header(std::FILE* f, const std::string& path) {
+  PlyHeader h;
+  std::vector<std::string> names;
+  char buf[512];
+  bool finished = false;
+  while (std::fgets(buf, sizeof(buf), f)) {
+    std::string line(buf);
+    while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
     if (line == "end_header") {
-      header_done = true;
+      finished = true;
       break;
     }
-    std::stringstream sst(line);
-    std::string token;
-    sst >> token;
-    if (token == "element") {
-      std::string what, count;
-      sst >> what >> count;
-      if (what != "vertex") {
-        std::cerr << "error: invalid ply format (line=" << line << ")" << std::endl;
-        return {};
+    char key[32] = {0}, a[64] = {0}, b[64] = {0};
+    const int got = std::sscanf(line.c_str(), "%31s %63s %63s", key, a, b);
+    if (got >= 3 && std::strcmp(key, "element") == 0) {
+      if (std::strcmp(a, "vertex") != 0) {  // faces etc.: not a plain point cloud
+        std::fprintf(stderr, "error: %s: unsupported ply element (%s)\n", path.c_str(), line.c_str());
+        return h;
       }
-      try {
-        n = static_cast<size_t>(std::stoull(count));
-      } catch (const std::exception&) {
-        std::cerr << "error: invalid ply format (line=" << line << ")" << std::endl;
-        return {};
+      char* end = nullptr;
+      h.vertices = static_cast<size_t>(std::strtoull(b, &end, 10));
+      if (end == b) {
+        std::fprintf(stderr, "error: %s: bad vertex count (%s)\n", path.c_str(), line.c_str());
+        return h;
       }
-    } else if (token == "property") {
-      std::string type, name;
-      sst >> type >> name;
-      if (type != "float") {
-        std::cerr << "error: only float properties are supported!! (line=" << line << ")" << std::endl;
-        return {};
+    } else if (got >= 3 && std::strcmp(key, "property") == 0) {
+      if (std::strcmp(a, "float") != 0 && std::strcmp(a, "float32") != 0) {
+        std::fprintf(stderr, "error: %s: only float properties are supported (%s)\n", path.c_str(), line.c_str());
+        return h;
       }
-      properties.push_back(name);
+      names.emplace_back(b);
     }
   }
-  auto is_axis = [&](size_t k, char c) { return properties[k].size() == 1 && std::tolower(static_cast<unsigned char>(properties[k][0])) == c; };
-  if (!header_done || properties.size() < 3 || !is_axis(0, 'x') || !is_axis(1, 'y') || !is_axis(2, 'z')) {
-    std::cerr << "error: invalid ply header or properties (the first three must be float x, y, z)" << std::endl;
-    return {};
+  auto axis = [&](size_t k, char lower) { return names[k].size() == 1 && (names[k][0] | 0x20) == lower; };
+  if (!finished || names.size() < 3 || !axis(0, 'x') || !axis(1, 'y') || !axis(2, 'z')) {
+    std::fprintf(stderr, "error: %s: header incomplete or the first three properties are not x y z\n", path.c_str());
+    return h;
   }
-  const size_t stride = properties.size();
-  std::vector<float> buffer(stride * n);
-  ifs.read(reinterpret_cast<char*>(buffer.data()), static_cast<std::streamsize>(sizeof(float) * buffer.size()));
-  if (static_cast<size_t>(ifs.gcount()) != sizeof(float) * buffer.size()) {
-    std::cerr << "error: truncated vertex data in " << filename << std::endl;
-    return {};
-  }
-  std::vector<Vector4f> points(n);
-  for (size_t i = 0; i < n; i++) points[i] = Vector4f{buffer[i * stride + 0], buffer[i * stride + 1], buffer[i * stride + 2], 1.0f};
-  return points;
+  h.floats_per_vertex = names.size();
+  h.ok = true;
+  return h;
 }
 
-/// PointCloud from raw single-precision points (the reference's `std::make_shared<PointCloud>(points)`, point_cloud.hpp:24-35)
-inline PointCloud::Ptr make_point_cloud(const std::vector<Vector4f>& points) {
+}  // namespace detail
+
+inline std::vector<Vector4f> read_ply(const std::string& filename) {
+  detail::File f = detail::open_file(filename, "rb");
+  if (!f) return {};
+  const detail::PlyHeader h = detail::parse_ply_header(f.get(), filename);
+  if (!h.ok) return {};
+  std::vector<float> raw(h.vertices * h.floats_per_vertex);
+  if (std::fread(raw.data(), sizeof(float), raw.size(), f.get()) != raw.size()) {
+    std::fprintf(stderr, "error: %s: vertex data shorter than the header promises\n", filename.c_str());
+    return {};
+  }
+  std::vector<Vector4f> cloud(h.vertices);
+  const float* src = raw.data();
+  for (Vector4f& p : cloud) {
+    p = {src[0], src[1], src[2], 1.0f};
+    src += h.floats_per_vertex;
+  }
+  return cloud;
+}
+
+inline std::vector<Vector4f> read_points(const std::string& filename) {
+  detail::File f = detail::open_file(filename, "rb");
+  if (!f) return {};
+  std::fseek(f.get(), 0, SEEK_END);
+  const long bytes = std::ftell(f.get());
+  std::fseek(f.get(), 0, SEEK_SET);
+  std::vector<Vector4f> cloud(bytes > 0 ? static_cast<size_t>(bytes) / sizeof(Vector4f) : 0);  // a trailing partial record is ignored
+  if (!cloud.empty() && std::fread(cloud.data(), sizeof(Vector4f), cloud.size(), f.get()) != cloud.size()) {
+    std::fprintf(stderr, "error: %s: short read\n", filename.c_str());
+    return {};
+  }
+  for (Vector4f& p : cloud) p[3] = 1.0f;  // the intensity slot becomes the homogeneous coordinate
+  return cloud;
+}
+
+inline void write_points(const std::string& filename, const std::vector<Vector4f>& cloud) {
+  detail::File f = detail::open_file(filename, "wb");
+  if (!f) return;
+  if (std::fwrite(cloud.data(), sizeof(Vector4f), cloud.size(), f.get()) != cloud.size()) std::fprintf(stderr, "error: %s: short write\n", filename.c_str());
+}
+
+/// PointCloud from raw single-precision points (what `std::make_shared<PointCloud>(points)` does in the reference, point_cloud.hpp:24-35)
+inline PointCloud::Ptr make_point_cloud(const std::vector<Vector4f>& raw) {
   auto cloud = std::make_shared<PointCloud>();
-  cloud->resize(points.size());
-  for (size_t i = 0; i < points.size(); i++) cloud->points[i] = vec4(points[i][0], points[i][1], points[i][2], 1.0);
+  cloud->resize(raw.size());
+  for (size_t i = 0; i < raw.size(); i++) cloud->points[i] = vec4(raw[i][0], raw[i][1], raw[i][2], 1.0);
   return cloud;
 }
 
