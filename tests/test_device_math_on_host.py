@@ -154,3 +154,62 @@ def test_rejector_is_strict_on_the_fp64_residual(hm, golden_prepared):
         assert hm.sgbm_linearize_pairs(0, 0, ctypes.c_double(1.0), ctypes.c_double(max_d2), _p(_colmajor(np.eye(4))), _p(z3), _p(z3), ctypes.c_size_t(1),
                                        _p(one[0]), _p(zc), _p(one[1]), _p(zn), _p(zc), 0, _p(out), None) == 0
         assert int(out[43]) == kept
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_kernel_arithmetic_on_random_inputs(hm, seed):
+    """Beyond the golden clouds: arbitrary rotations (not just small ones), clouds hundreds of metres from the origin (the centring is what
+    keeps FP32 storage accurate there), covariances with the reference's (1e-3, 1, 1) spectrum in random orientations, robust-kernel widths
+    that put points on both sides of the Huber knee, and a rejector radius that cuts through the residual distribution."""
+    rng = np.random.default_rng(100 + seed)
+    n = 4000
+    offset = rng.uniform(-400, 400, 3)
+    tp = np.c_[rng.uniform(-30, 30, (n, 3)) + offset, np.ones(n)]
+    T = np.eye(4)
+    T[:3, :3] = _random_rotation(rng)
+    T[:3, 3] = rng.uniform(-5, 5, 3)
+    res = rng.normal(0, 0.3, (n, 3))  # residual target - T * source
+    sp = np.c_[(tp[:, :3] - res - T[:3, 3]) @ T[:3, :3], np.ones(n)]  # R^T (q - t)
+
+    def covs():
+        out = np.zeros((n, 4, 4))
+        for i in range(n):
+            V = _random_rotation(rng)
+            out[i, :3, :3] = V @ np.diag([1e-3, 1.0, 1.0]) @ V.T
+        return out
+
+    scv, tcv = covs(), covs()
+    tn = np.c_[np.stack([_random_rotation(rng)[:, 0] for _ in range(n)]), np.zeros(n)]
+
+    P = Pairs.__new__(Pairs)  # matched pairs given directly, not taken from the golden clouds
+    P.sp, P.sc, P.tp, P.tn, P.tcv, P.n = sp, scv, tp, tn, tcv, n
+    P.cs = 0.5 * (sp[:, :3].min(0) + sp[:, :3].max(0))
+    P.ct = 0.5 * (tp[:, :3].min(0) + tp[:, :3].max(0))
+    spm, scm, tpm, tnm, tcm = storage_model(P)
+    d2 = (((spm[:, :3] @ T[:3, :3].T + T[:3, 3]) - tpm[:, :3]) ** 2).sum(1)
+    max_d2 = float(np.quantile(d2, 0.8))
+    keep = d2 <= max_d2
+    clear = np.abs(d2 - max_d2) > 1e-9
+    ident = np.arange(n).astype(np.uint64)
+    corr = np.where(keep, ident, NF.NO)
+    for factor in (0, 1, 2):
+        for robust, c in ((0, 1.0), (1, 0.35), (2, 0.5)):
+            for frame in (0, 1):
+                H, b, e, n_in, acc = P.linearize(hm, T, factor, robust, c, max_d2, frame, want_accepted=(frame == 0))
+                if frame == 0:
+                    assert np.array_equal(acc[clear].astype(bool), keep[clear])
+                assert abs(n_in - int(keep.sum())) <= int((~clear).sum())
+                H2, b2, e2 = NF.linearize(T, corr, factor, robust, c, spm, scm, tpm, tnm, tcm)
+                assert np.linalg.norm(H - H2) <= 1e-9 * np.linalg.norm(H2), (factor, robust, frame)
+                assert abs(e - e2) <= 1e-9 * e2 and np.abs(b - b2).max() <= 1e-9 * np.sqrt(2 * e2 * np.diag(H2)).max()
+            T2 = T @ O.se3_exp(rng.normal(0, 0.02, 6))
+            e_t = P.error(hm, T2, T, factor, robust, c)
+            assert abs(e_t - NF.error(T2, T, ident, factor, robust, c, spm, scm, tpm, tnm, tcm)) <= 1e-9 * e_t
