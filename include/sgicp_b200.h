@@ -77,6 +77,18 @@ int sgb_comm_connect(sgb_ctx* ctx, int rank, int world, const void* handles);
 int sgb_comm_mailbox(sgb_ctx* ctx, void** out_device_ptr);
 int sgb_comm_connect_ptrs(sgb_ctx* ctx, int rank, int world, void* const* mailboxes);
 int sgb_comm_disconnect(sgb_ctx* ctx);
+/* How long a rank waits for a peer before it gives up on an exchange (default 5000 ms). */
+int sgb_comm_set_timeout_ms(sgb_ctx* ctx, int milliseconds);
+/* Failure handling of the fused exchange.  A rank that gives up on a peer (timeout), or that hears from a peer that its call failed on
+ * the host, gets NaN sums AND a sticky status word: the host-returning calls (sgb_linearize, sgb_error) then return a non-zero code
+ * (4), every later collective call of the context returns 5 until sgb_comm_connect* is called again.  Users of the *_device variants
+ * read the status themselves: 0 = fine, bit 0 = timeout, bit 1 = a peer reported a failed call.  A call that fails on the host of one
+ * rank (bad argument, missing covariances) still takes part in the exchange -- it tells the peers instead of leaving them waiting. */
+int sgb_comm_status(sgb_ctx* ctx, int* out_status);
+/* Diagnostics: nanoseconds this rank's finishing CTA waited for its slowest peer in each of the last 64 exchanges (ring indexed by
+ * call number % 64; *out_calls = exchanges so far).  The rank that arrives last sees the bare transport latency, the first one skew
+ * + transport: the minimum and maximum over the ranks separate the two (bench.py `comm_wait_us`). */
+int sgb_comm_wait_ns(sgb_ctx* ctx, uint64_t* out_ring64, uint64_t* out_calls);
 
 /* ---- target: replaces traits::point/normal/cov(target, k) (points/traits.hpp:38-54) and the
  *      target_tree argument of Reduction::linearize (reduction.hpp:23) -------------------------- */
@@ -92,7 +104,7 @@ int sgb_target_set_kdtree(sgb_ctx* ctx, const void* nodes24, size_t n_nodes, uin
  * per level along the widest axis of every node's box -- a balanced median-split kd-tree with at most 32 points per leaf
  * (one per lane of the warp-cooperative leaf scan; the reference's builder uses 20), stored implicitly.  Asynchronous on
  * the context's stream, no host round trip.  Exact nearest-neighbour results do not depend on the split choices (only
- * exact ties can).  max_leaf_size is honoured only by the host-side profiling builder (SGB_TREE=host). */
+ * exact ties can).  max_leaf_size is accepted for source compatibility with KdTreeBuilder::max_leaf_size and ignored. */
 int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size);
 /* Gaussian voxel map target (VGICP): replaces IncrementalVoxelMap<GaussianVoxel>::nearest_neighbor_search
  * (ann/incremental_voxelmap.hpp:99-119) and its point/cov traits (:207-222).  Voxel i of the arrays is
@@ -134,6 +146,11 @@ int sgb_error(sgb_ctx* ctx, const double* T_colmajor16, double* out_e);
 int sgb_linearize_device(sgb_ctx* ctx, int factor_kind, int robust_kind, double robust_c, int rejector_kind, double max_dist_sq,
                          const double* T_colmajor16, double* d_out44);
 int sgb_error_device(sgb_ctx* ctx, const double* T_colmajor16, double* d_out1);
+
+/* Forget the correspondences of the previous linearize as search seeds: the next sgb_linearize searches like the first iteration of a
+ * fresh align() (the seeds only ever prune -- results are identical with or without them; this exists so that a benchmark can time an
+ * unseeded first iteration without re-uploading the source). */
+int sgb_drop_seeds(sgb_ctx* ctx);
 
 /* factors[i].target_index of the last linearize, in the caller's source order
  * (SGB_NO_CORRESPONDENCE = rejected; icp_factor.hpp:66-69). */

@@ -31,6 +31,10 @@ _SIGNATURES = {
     "sgb_comm_mailbox": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sgb_comm_connect_ptrs": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "sgb_comm_disconnect": (C.c_int, [_vp]),
+    "sgb_comm_set_timeout_ms": (C.c_int, [_vp, C.c_int]),
+    "sgb_comm_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "sgb_comm_wait_ns": (C.c_int, [_vp, _u64p, _u64p]),
+    "sgb_drop_seeds": (C.c_int, [_vp]),
     "sgb_target_set_points": (C.c_int, [_vp, C.c_size_t, _dp, _dp, _dp]),
     "sgb_target_set_kdtree": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _u64p]),
     "sgb_target_build_kdtree": (C.c_int, [_vp, C.c_int]),
@@ -57,21 +61,22 @@ class SgbError(RuntimeError):
     pass
 
 
-def library_path():
-    return os.path.join(_HERE, "lib", "libsgicp_b200.so")
+def library_path(profiling=False):
+    """the product library; profiling=True: the same sources built with -DSGB_PROFILING (experiment switches read from SGB_*
+    environment variables in sgb_create + the superseded A/B kernels) -- A/B scripts and the structure-agreement test only"""
+    return os.path.join(_HERE, "lib", "libsgicp_b200_prof.so" if profiling else "libsgicp_b200.so")
 
 
 def exported_symbols():
     return sorted(_SIGNATURES)
 
 
-_LIB = None
+_LIBS = {}
 
 
-def _lib():
-    global _LIB
-    if _LIB is None:
-        path = library_path()
+def _lib(profiling=False):
+    if profiling not in _LIBS:
+        path = library_path(profiling)
         if not os.path.exists(path):
             raise SgbError(
                 f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -82,8 +87,8 @@ def _lib():
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        _LIB = L
-    return _LIB
+        _LIBS[profiling] = L
+    return _LIBS[profiling]
 
 
 def _f64(a):
@@ -111,8 +116,10 @@ def _points4(p):
 class Context:
     """One GPU, one stream (sgb_ctx)."""
 
-    def __init__(self, device=0):
-        self._L = _lib()
+    def __init__(self, device=0, profiling=None):
+        if profiling is None:  # A/B scripts select the profiling build for a whole process
+            profiling = os.environ.get("SGB_LIBRARY", "") == "prof"
+        self._L = _lib(bool(profiling))
         h = _vp()
         rc = self._L.sgb_create(int(device), C.byref(h))
         if rc != 0:
@@ -259,6 +266,25 @@ class Context:
 
     def comm_disconnect(self):
         self._check(self._L.sgb_comm_disconnect(self._h))
+
+    def comm_set_timeout_ms(self, ms):
+        self._check(self._L.sgb_comm_set_timeout_ms(self._h, int(ms)))
+
+    def comm_status(self):
+        """0 = fine, bit 0 = an exchange gave up on a peer, bit 1 = a peer reported a failed call (sticky until the next connect)"""
+        st = C.c_int(0)
+        self._check(self._L.sgb_comm_status(self._h, C.byref(st)))
+        return int(st.value)
+
+    def comm_wait_ns(self):
+        """(ring of the last 64 exchanges' waiting times in ns indexed by call number % 64, number of exchanges so far)"""
+        ring = np.zeros(64, dtype=np.uint64)
+        calls = C.c_uint64(0)
+        self._check(self._L.sgb_comm_wait_ns(self._h, ring.ctypes.data_as(_u64p), C.byref(calls)))
+        return ring, int(calls.value)
+
+    def drop_seeds(self):
+        self._check(self._L.sgb_drop_seeds(self._h))
 
     def num_inliers(self):
         n = C.c_size_t(0)

@@ -56,9 +56,11 @@ int upload_tree(sgb_ctx* ctx, const FlatTree& tree, const float* host_pts_xyzw) 
   if (pending > 40) return fail(ctx, 1, "kd-tree too deep for the device traversal stack (depth > 40)");
   CU(ctx->tgt_pnodes.reserve(pnodes.size() * sizeof(PacketNode)));
   CU(cudaMemcpyAsync(ctx->tgt_pnodes.p, pnodes.data(), pnodes.size() * sizeof(PacketNode), cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx->tgt_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
   CU(ctx->tgt_perm.reserve(tree.perm.size() * sizeof(uint32_t)));
+#ifdef SGB_PROFILING  // the 8-byte kd nodes are only walked by the per-thread / fused A/B kernels
+  CU(ctx->tgt_nodes.reserve(tree.nodes.size() * sizeof(FlatNode)));
   CU(cudaMemcpyAsync(ctx->tgt_nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, ctx->stream));
+#endif
   CU(cudaMemcpyAsync(ctx->tgt_perm.p, tree.perm.data(), tree.perm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   const size_t n = ctx->n_tgt;
   CU(ctx->tgt_pts.reserve(n * sizeof(float4)));
@@ -78,6 +80,7 @@ int upload_tree(sgb_ctx* ctx, const FlatTree& tree, const float* host_pts_xyzw) 
   ctx->tgt_has_kd = true;
   ctx->tgt_is_voxel = false;
   ctx->tgt_ready = true;
+  ctx->tgt_feats_leaf_only = false;
   ctx->have_lin = false;
   ctx->corr_seeds = false;
   ctx->n_pnodes = pnodes.size();
@@ -112,11 +115,13 @@ int fill_params(sgb_ctx* ctx, LinParams& P, const double* T_colmajor16) {
     for (int p = 0; p < ctx->comm_world; p++) P.comm.mail[p] = ctx->comm_peers[p];
     P.comm.seq = ++ctx->comm_seq;  // exactly one reduction per fill_params (do_linearize / do_error)
     P.comm.timeout_ns = ctx->comm_timeout_ns;
+    P.comm.status = ctx->comm_status.as<unsigned int>();
+    P.comm.stamps = reinterpret_cast<unsigned long long*>(ctx->comm_status.as<unsigned char>() + 64);
   }
   return 0;
 }
 
-int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* d_out) {
+int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* d_out) {
   if (factor < 0 || factor > 2 || robust < 0 || robust > 2 || rejector < 0 || rejector > 1) return fail(ctx, 1, "sgb_linearize: invalid factor/robust/rejector kind");
   if (!T) return fail(ctx, 1, "sgb_linearize: null pose");
   CU(cudaSetDevice(ctx->device));
@@ -129,6 +134,9 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
       P0.out = d_out;
       CU(launch_reduce_nothing(P0, true, ctx->stream));
       ctx->launches += 1;
+    } else if (d_out == ctx->h_out_dev) {  // the mapped host slot of sgb_linearize: clear it from the host side, in stream order
+      CU(cudaStreamSynchronize(ctx->stream));
+      std::memset(ctx->h_out, 0, 44 * sizeof(double));
     } else {
       CU(cudaMemsetAsync(d_out, 0, 44 * sizeof(double), ctx->stream));
     }
@@ -172,12 +180,19 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
   P.use_prev = (ctx->corr_seeds && !ctx->tgt_is_voxel) ? 1 : 0;
   P.robust_c = robust_c;
   P.out = d_out;
-  if (ctx->search_mode != 0 && !ctx->tgt_is_voxel) {
+#ifdef SGB_PROFILING
+  const bool split_path = ctx->search_mode != 0 && !ctx->tgt_is_voxel;
+  const bool packet_path = ctx->search_mode == 2 && ctx->src_run == 1;
+#else
+  const bool split_path = !ctx->tgt_is_voxel;
+  const bool packet_path = true;
+#endif
+  if (split_path) {
     // phase 1: search at high occupancy; phase 2: factor algebra + reduction (sgb_kernels_split.cu)
     const uint32_t chunk_pts = 32u * ctx->src_run;
     const size_t n_chunks = (ctx->n_src + chunk_pts - 1) / chunk_pts;
     int sgrid = static_cast<int>((n_chunks * 32 + kLinBlock - 1) / kLinBlock);
-    if (ctx->search_mode == 2 && ctx->src_run == 1) {
+    if (packet_path) {
       const int scap = ctx->sm_count * packet_occupancy(depth);
       if (sgrid > scap) sgrid = scap;
       const uint8_t* settled = nullptr;
@@ -222,16 +237,20 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
         ctx->packet_parity ^= 1;
       }
       CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, ctx->stream));
+#ifdef SGB_PROFILING
       if (ctx->debug_pending && pending_count) {  // profiling aid: synchronises
         uint32_t h = 0;
         CU(cudaMemcpyAsync(&h, pending_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         std::fprintf(stderr, "[sgb] grid front end: %u of %zu queries pending (cell %.4g)\n", h, ctx->n_src, ctx->grid_cell);
       }
+#endif
     } else {
+#ifdef SGB_PROFILING
       const int scap = ctx->sm_count * search_occupancy(depth);
       if (sgrid > scap) sgrid = scap;
       CU(launch_search(P, sgrid, depth, ctx->stream));
+#endif
     }
     // exactly one wave of the factor kernel (its CTAs loop over tiles)
     int fgrid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
@@ -256,7 +275,7 @@ int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int reje
   return 0;
 }
 
-int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
+int do_error_impl(sgb_ctx* ctx, const double* T, double* d_out) {
   if (!T) return fail(ctx, 1, "sgb_error: null pose");
   if (!ctx->have_lin) return fail(ctx, 1, "sgb_error: no preceding sgb_linearize (the correspondences are cached there)");
   CU(cudaSetDevice(ctx->device));
@@ -268,6 +287,9 @@ int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
       P0.out = d_out;
       CU(launch_reduce_nothing(P0, false, ctx->stream));
       ctx->launches += 1;
+    } else if (d_out == ctx->h_out_dev + 48) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      ctx->h_out[48] = 0.0;
     } else {
       CU(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
     }
@@ -285,6 +307,54 @@ int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
   CU(launch_error(P, ctx->lin_factor, ctx->lin_robust, grid, ctx->stream));
   ctx->launches += 1;
   return 0;
+}
+
+
+// With the fused multi-GPU exchange every rank must issue the same sequence of collective reductions.  A call that fails on the
+// host of ONE rank (bad argument, missing covariances, a CUDA error) before its reduction kernel was launched would leave that rank
+// one sequence number behind its peers for good: they would spin into the timeout, and every later exchange would mismatch.
+// The wrappers therefore make a failed call collective-safe: the rank still takes its sequence number and launches a one-CTA
+// kernel that tells the peers "nothing valid from me" (kCommPoison) -- they get NaN + a non-zero status immediately instead of a
+// timeout -- and the context refuses further work until sgb_comm_connect* is called again.
+int comm_poison(sgb_ctx* ctx, const double* T, double* d_out, bool linearize) {
+  static const double identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const std::string first_error = ctx->err;
+  ctx->comm_failed = true;
+  if (ensure_reduction_buffers(ctx, 1) == 0 && d_out) {
+    LinParams P0;
+    fill_params(ctx, P0, T ? T : identity);
+    P0.comm.poison = 1;
+    P0.out = d_out;
+    if (launch_reduce_nothing(P0, linearize, ctx->stream) == cudaSuccess) ctx->launches += 1;
+  }
+  ctx->err = first_error + " [multi-GPU: the peers were told; call sgb_comm_connect again before the next collective call]";
+  return 0;
+}
+
+int do_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int rejector, double max_dist_sq, const double* T, double* d_out) {
+  if (ctx->comm_failed) return fail(ctx, 5, "sgb_linearize: an earlier multi-GPU exchange of this context failed; call sgb_comm_connect again");
+  const unsigned long long seq0 = ctx->comm_seq;
+  const int rc = do_linearize_impl(ctx, factor, robust, robust_c, rejector, max_dist_sq, T, d_out);
+  if (rc != 0 && ctx->comm_world > 1 && ctx->comm_seq == seq0) comm_poison(ctx, T, d_out, true);
+  return rc;
+}
+
+int do_error(sgb_ctx* ctx, const double* T, double* d_out) {
+  if (ctx->comm_failed) return fail(ctx, 5, "sgb_error: an earlier multi-GPU exchange of this context failed; call sgb_comm_connect again");
+  const unsigned long long seq0 = ctx->comm_seq;
+  const int rc = do_error_impl(ctx, T, d_out);
+  if (rc != 0 && ctx->comm_world > 1 && ctx->comm_seq == seq0) comm_poison(ctx, T, d_out, false);
+  return rc;
+}
+
+// after a host-visible result of a collective call has arrived: did the exchange behind it give up on / hear a failure from a peer?
+int comm_check(sgb_ctx* ctx, const char* who) {
+  if (ctx->comm_world <= 1) return 0;
+  const unsigned int st = *reinterpret_cast<volatile unsigned int*>(ctx->h_out + 60);
+  if (st == 0) return 0;
+  ctx->comm_failed = true;
+  return fail(ctx, 4, std::string(who) + ((st & 2u) ? ": a peer rank reported a failed call" : ": gave up waiting for a peer rank (timeout)") +
+                          "; the sums are NaN -- call sgb_comm_connect again on every rank");
 }
 
 }  // namespace
@@ -325,13 +395,17 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   ctx->device = device_id;
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_out), 64 * sizeof(double));
+  // result slot in MAPPED page-locked host memory: the finishing CTA of a reduction writes H|b|e straight into it over PCIe, so the
+  // host-returning calls (sgb_linearize / sgb_error) need no device-to-host copy behind the kernel, just the stream synchronisation
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_out), 64 * sizeof(double), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_out_dev), ctx->h_out, 0);
   if (e != cudaSuccess) {
     g_create_error = std::string("sgb_create: ") + cudaGetErrorString(e);
     delete ctx;
     return 2;
   }
   ctx->stream = ctx->own_stream;
+#ifdef SGB_PROFILING  // libsgicp_b200_prof.so only: the A/B switches behind the experiment log in profiles/ (the product library reads no environment variable)
   if (const char* s = getenv("SGB_SEARCH")) ctx->search_mode = atoi(s);  // profiling switch (profiles/r01): 0 fused, 1 per-thread, 2 packet
   if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
   if (const char* s = getenv("SGB_GRID")) ctx->use_grid = !(s[0] == '0');  // profiling switch: 0 = tree search only
@@ -346,12 +420,12 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_PROBE_TAIL")) ctx->probe_batch_tail = (s[0] == '1');        // 1 = probe scans its list in clamped batches of eight (A/B, sgb_grid.cu)
   if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
   ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
-  if (const char* s = getenv("SGB_COMM_TIMEOUT_MS")) ctx->comm_timeout_ns = static_cast<unsigned long long>(std::max(1, atoi(s))) * 1000000ull;
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
     ctx->host_tree = (s[0] == 'h');
     if (s[0] == 'l') ctx->tree_quality = 0;
   }
   if (ctx->search_mode != 2) ctx->host_tree = true;                        // the per-thread / fused kernels walk 8-byte kd nodes
+#endif
   *out_ctx = ctx;
   return 0;
 }
@@ -391,6 +465,8 @@ static int comm_ensure_mailbox(sgb_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   CU(ctx->comm_mail.reserve(kMailBytes));
   CU(cudaMemset(ctx->comm_mail.p, 0, ctx->comm_mail.cap));  // flags = 0: no call has sequence number 0
+  CU(ctx->comm_status.reserve(64 + kCommStampRing * sizeof(unsigned long long)));  // [0]: sticky status word, [64..]: wait-time ring
+  CU(cudaMemset(ctx->comm_status.p, 0, ctx->comm_status.cap));
   return 0;
 }
 
@@ -422,6 +498,38 @@ int sgb_comm_disconnect(sgb_ctx* ctx) {
   }
   ctx->comm_world = 0;
   ctx->comm_rank = 0;
+  ctx->comm_failed = false;
+  return 0;
+}
+
+int sgb_comm_set_timeout_ms(sgb_ctx* ctx, int milliseconds) {
+  if (!ctx) return 1;
+  if (milliseconds < 1) return fail(ctx, 1, "sgb_comm_set_timeout_ms: need a positive time");
+  ctx->comm_timeout_ns = static_cast<unsigned long long>(milliseconds) * 1000000ull;
+  return 0;
+}
+
+int sgb_comm_status(sgb_ctx* ctx, int* out_status) {
+  if (!ctx || !out_status) return 1;
+  *out_status = 0;
+  if (!ctx->comm_status.p) return 0;
+  CU(cudaSetDevice(ctx->device));
+  unsigned int st = 0;
+  CU(cudaMemcpyAsync(&st, ctx->comm_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (st) ctx->comm_failed = true;
+  *out_status = static_cast<int>(st);
+  return 0;
+}
+
+int sgb_comm_wait_ns(sgb_ctx* ctx, uint64_t* out_ring64, uint64_t* out_calls) {
+  if (!ctx || !out_ring64) return 1;
+  std::memset(out_ring64, 0, kCommStampRing * sizeof(uint64_t));
+  if (out_calls) *out_calls = ctx->comm_seq;
+  if (!ctx->comm_status.p) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(out_ring64, ctx->comm_status.as<unsigned char>() + 64, kCommStampRing * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -438,6 +546,8 @@ int sgb_comm_connect_ptrs(sgb_ctx* ctx, int rank, int world, void* const* mailbo
   // a fresh epoch: clear the flags and restart the sequence (every rank does the same before its first exchange;
   // the caller separates connect from the first linearize by a barrier, as with any communicator construction)
   CU(cudaMemset(ctx->comm_mail.p, 0, ctx->comm_mail.cap));
+  CU(cudaMemset(ctx->comm_status.p, 0, ctx->comm_status.cap));
+  ctx->comm_failed = false;
   ctx->comm_seq = 0;
   ctx->comm_world = world;
   ctx->comm_rank = rank;
@@ -546,7 +656,13 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
     return 0;
   }
   CU(cudaSetDevice(ctx->device));
-  if (ctx->search_mode == 2 && !ctx->host_tree) {
+#ifdef SGB_PROFILING
+  const bool device_build = ctx->search_mode == 2 && !ctx->host_tree;
+#else
+  const bool device_build = true;
+  (void)max_leaf_size;
+#endif
+  if (device_build) {
     // device-side construction (linear BVH over the Hilbert order, sgb_kernels.cu): no host round trip, fully asynchronous
     const size_t n = ctx->n_tgt;
     int depth = 1;
@@ -567,11 +683,15 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
     ctx->tgt_has_kd = false;
     ctx->tgt_is_voxel = false;
     ctx->tgt_ready = true;
+    ctx->tgt_feats_leaf_only = false;
     ctx->have_lin = false;
     ctx->corr_seeds = false;
     ctx->n_pnodes = (static_cast<size_t>(1) << (depth - 1)) - 1;  // P - 1 records of the implicit tree (depth = log2(P) + 1)
     return build_grid(ctx);
   }
+#ifndef SGB_PROFILING
+  return fail(ctx, 1, "sgb_target_build_kdtree: unreachable");
+#else
   std::vector<float> pts(ctx->n_tgt * 4);
   CU(cudaMemcpyAsync(pts.data(), ctx->tgt_orig_pts.p, ctx->n_tgt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -579,6 +699,7 @@ int sgb_target_build_kdtree(sgb_ctx* ctx, int max_leaf_size) {
   std::string err;
   if (!build_flat_tree(pts.data(), ctx->n_tgt, max_leaf_size, tree, err)) return fail(ctx, 1, "sgb_target_build_kdtree: " + err);
   return upload_tree(ctx, tree, pts.data());
+#endif
 }
 
 int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, const int32_t* coords, const double* means, const double* covs, int search_offsets) {
@@ -649,6 +770,7 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   ctx->src_has_covs = covs != nullptr;
   ctx->have_lin = false;
   ctx->corr_seeds = false;
+  ctx->src_orig_valid = n > 0;  // tmp_pts (filled below) holds this source in original order
   CU(ctx->src_centre.reserve(4 * sizeof(double)));
   CU(ctx->src_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
@@ -692,7 +814,9 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   // chunk-transposed Morton order: a lane walks K consecutive points of the curve, warp loads stay coalesced.
   // K shrinks for small clouds so that there are still enough 32*K-point work units to fill the GPU.
   uint32_t K = 1;
-  if (const char* s = getenv("SGB_RUN")) K = static_cast<uint32_t>(atoi(s)) > 0 ? static_cast<uint32_t>(atoi(s)) : 1;  // profiling switch
+#ifdef SGB_PROFILING
+  if (const char* s = getenv("SGB_RUN")) K = static_cast<uint32_t>(atoi(s)) > 0 ? static_cast<uint32_t>(atoi(s)) : 1;  // chunk-transposed layout of the per-thread search (A/B)
+#endif
   while (K > 1 && n / (32ull * K) < static_cast<size_t>(ctx->sm_count) * 16) K >>= 1;
   ctx->src_run = K;
   if (K > 1) {
@@ -718,10 +842,11 @@ int sgb_linearize(sgb_ctx* ctx, int factor, int robust, double robust_c, int rej
   if (!ctx) return 1;
   if (!out_Hbe43) return fail(ctx, 1, "sgb_linearize: null output");
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->out44.reserve(64 * sizeof(double)));
-  if (int rc = do_linearize(ctx, factor, robust, robust_c, rejector, max_dist_sq, T, ctx->out44.as<double>())) return rc;
-  CU(cudaMemcpyAsync(ctx->h_out, ctx->out44.p, 44 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // the finishing CTA writes H|b|e|inliers straight into the mapped host slot: no copy behind the kernel
+  if (int rc = do_linearize(ctx, factor, robust, robust_c, rejector, max_dist_sq, T, ctx->h_out_dev)) return rc;
+  if (ctx->comm_world > 1) CU(cudaMemcpyAsync(ctx->h_out + 60, ctx->comm_status.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (int rc = comm_check(ctx, "sgb_linearize")) return rc;
   std::memcpy(out_Hbe43, ctx->h_out, 43 * sizeof(double));
   return 0;
 }
@@ -736,11 +861,11 @@ int sgb_error(sgb_ctx* ctx, const double* T, double* out_e) {
   if (!ctx) return 1;
   if (!out_e) return fail(ctx, 1, "sgb_error: null output");
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->out44.reserve(64 * sizeof(double)));
-  double* d_e = ctx->out44.as<double>() + 48;  // keep H|b|e|inliers of the last linearize intact
+  double* d_e = ctx->h_out_dev + 48;  // mapped host slot; H|b|e|inliers of the last linearize stay intact in [0, 44)
   if (int rc = do_error(ctx, T, d_e)) return rc;
-  CU(cudaMemcpyAsync(ctx->h_out + 48, d_e, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->comm_world > 1) CU(cudaMemcpyAsync(ctx->h_out + 60, ctx->comm_status.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (int rc = comm_check(ctx, "sgb_error")) return rc;
   *out_e = ctx->h_out[48];
   return 0;
 }
@@ -764,9 +889,20 @@ int sgb_num_inliers(sgb_ctx* ctx, size_t* n) {
   if (!ctx || !n) return 1;
   if (!ctx->have_lin || !ctx->last_out) return fail(ctx, 1, "sgb_num_inliers: no preceding sgb_linearize");
   CU(cudaSetDevice(ctx->device));
+  if (ctx->last_out == ctx->h_out_dev) {  // sgb_linearize left the count in the mapped host slot
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n = static_cast<size_t>(ctx->h_out[43] + 0.5);
+    return 0;
+  }
   CU(cudaMemcpyAsync(ctx->h_out + 56, ctx->last_out + 43, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *n = static_cast<size_t>(ctx->h_out[56] + 0.5);
+  return 0;
+}
+
+int sgb_drop_seeds(sgb_ctx* ctx) {
+  if (!ctx) return 1;
+  ctx->corr_seeds = false;
   return 0;
 }
 

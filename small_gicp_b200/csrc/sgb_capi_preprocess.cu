@@ -195,6 +195,13 @@ int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   CU(launch_features(ctx->tgt_pnodes.as<float4>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->tgt_centre.as<double>(), 3,
                      ctx->tgt_normals.as<float4>(), ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->tree_depth, 1, ctx->stream));
   ctx->launches += 1;
+  // keep the ORIGINAL-order copies in step (a later sgb_target_build_kdtree / _set_kdtree re-gathers the leaf-ordered streams from them)
+  CU(ctx->tgt_orig_normals.reserve(n * sizeof(float4)));
+  CU(ctx->tgt_orig_covA.reserve(n * sizeof(float4)));
+  CU(ctx->tgt_orig_covB.reserve(n * sizeof(float4)));
+  CU(launch_scatter(ctx->tgt_perm.as<uint32_t>(), n, ctx->tgt_normals.as<float4>(), ctx->tgt_orig_normals.as<float4>(), ctx->tgt_covA.as<float4>(),
+                    ctx->tgt_orig_covA.as<float4>(), ctx->tgt_covB.as<float4>(), ctx->tgt_orig_covB.as<float4>(), ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
   return 0;
 }
 
@@ -208,6 +215,7 @@ int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   if (n == 0) return 0;
   CU(cudaSetDevice(ctx->device));
   // tmp_pts still holds the source in ORIGINAL order (centred FP32, w = index) from sgb_source_set_points
+  if (!ctx->src_orig_valid) return fail(ctx, 1, "sgb_source_estimate_features: no source points (call sgb_source_set_points first)");
   int depth = 0;
   if (int rc = build_lbvh(ctx, ctx->tmp_pts.as<float4>(), n, ctx->src_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
   CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
@@ -320,10 +328,10 @@ int sgb_target_build_voxelmap(sgb_ctx* ctx, size_t n, const double* points, cons
   // per-voxel mean / covariance / integer coordinates (FP64), then the same device-side conversion as sgb_target_set_voxelmap
   CU(ctx->pre_out_normals.reserve(static_cast<size_t>(n_vox) * 4 * sizeof(double)));
   if (covs) CU(ctx->pre_out_covs.reserve(static_cast<size_t>(n_vox) * 16 * sizeof(double)));
-  CU(ctx->tmp_pts.reserve(static_cast<size_t>(n_vox) * sizeof(int4)));
+  CU(ctx->pre_vox_coords.reserve(static_cast<size_t>(n_vox) * sizeof(int4)));  // NOT tmp_pts: that buffer holds the source in original order
   CU(launch_voxel_stats(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->pre_heads.as<uint32_t>(), ctx->pre_slots.as<uint32_t>(), n,
                         ctx->stage_pts.as<double>(), covs ? ctx->stage_covs.as<double>() : nullptr, ctx->pre_out_normals.as<double>(),
-                        covs ? ctx->pre_out_covs.as<double>() : nullptr, ctx->tmp_pts.as<int4>(), ctx->sm_count, ctx->stream));
+                        covs ? ctx->pre_out_covs.as<double>() : nullptr, ctx->pre_vox_coords.as<int4>(), ctx->sm_count, ctx->stream));
   CU(ctx->tgt_pts.reserve(static_cast<size_t>(n_vox) * sizeof(float4)));
   if (covs) {
     CU(ctx->tgt_covA.reserve(static_cast<size_t>(n_vox) * sizeof(float4)));
@@ -335,7 +343,7 @@ int sgb_target_build_voxelmap(sgb_ctx* ctx, size_t n, const double* points, cons
   uint32_t capacity = 16;
   while (capacity < 2ull * n_vox) capacity <<= 1;  // load factor <= 1/2
   CU(ctx->vox_table.reserve(static_cast<size_t>(capacity) * sizeof(int4)));
-  CU(launch_vox_table_build(ctx->tmp_pts.as<int4>(), n_vox, ctx->vox_table.as<int4>(), capacity, ctx->stream));
+  CU(launch_vox_table_build(ctx->pre_vox_coords.as<int4>(), n_vox, ctx->vox_table.as<int4>(), capacity, ctx->stream));
   ctx->launches += 7;
   ctx->vox_mask = capacity - 1;
   ctx->n_tgt = n_vox;

@@ -47,7 +47,9 @@ struct sgb_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  int search_mode = 2;  // 2: packet (warp-cooperative) search + factor kernel; 1: per-thread search + factor kernel; 0: single fused kernel
+  // The product library has ONE search path (grid front end + packet / pending search, then the factor kernel).  The fields below that
+  // select anything else are only ever changed by the profiling build (-DSGB_PROFILING, libsgicp_b200_prof.so: A/B runs in profiles/).
+  int search_mode = 2;  // 2: packet (warp-cooperative) search + factor kernel; [profiling build] 1: per-thread search + factor kernel; 0: single fused kernel
 
   // ---- target ----
   size_t n_tgt = 0;
@@ -92,10 +94,14 @@ struct sgb_ctx {
   sgb::DevBuf stage_pts, stage_normals, stage_covs;  // raw double uploads
   sgb::DevBuf tmp_pts, tmp_covA, tmp_covB, keys_in, keys_out, vals_in, sort_temp;
   sgb::DevBuf corr, partials, ticket, out44, corr64;
-  double* h_out = nullptr;  // pinned, 64 doubles
+  double* h_out = nullptr;      // page-locked AND mapped, 64 doubles: [0,44) H|b|e|inliers, [48] error(), [56] scratch, [60] comm status
+  double* h_out_dev = nullptr;  // device address of the same memory (the reduction's finishing CTA writes into it)
 
   // ---- preprocessing scratch (sgb_capi_preprocess.cu) ----
   sgb::DevBuf pre_pts, pre_leaf_pts, pre_nodes, pre_perm, pre_centre, pre_bounds, pre_out_normals, pre_out_covs, pre_heads, pre_slots, pre_vals_out;
+  sgb::DevBuf pre_vox_coords;  // integer voxel coordinates of sgb_target_build_voxelmap (its own scratch: tmp_pts belongs to the source)
+  bool src_orig_valid = false;  // tmp_pts holds the current source in original order (sgb_source_estimate_features needs it)
+  bool tgt_feats_leaf_only = false;  // normals / covariances were estimated on the device into the leaf-ordered streams only
 
   // ---- multi-GPU exchange fused into the reduction's finishing CTA (sgb_comm_*, CommParams in sgb_device.cuh) ----
   sgb::DevBuf comm_mail;                  // this rank's mailbox (zeroed at allocation)
@@ -103,7 +109,9 @@ struct sgb_ctx {
   bool comm_ipc_opened[8] = {};           // mapped by cudaIpcOpenMemHandle (to be closed)
   int comm_world = 0, comm_rank = 0;      // world <= 1: single GPU
   unsigned long long comm_seq = 0;        // collective calls issued so far
-  unsigned long long comm_timeout_ns = 5000000000ull;  // a peer that has not arrived after 5 s (SGB_COMM_TIMEOUT_MS) is given up on
+  unsigned long long comm_timeout_ns = 5000000000ull;  // a peer that has not arrived after 5 s (sgb_comm_set_timeout_ms) is given up on
+  sgb::DevBuf comm_status;                // one sticky word: != 0 after an exchange gave up on a peer (read back with every host-visible result)
+  bool comm_failed = false;               // host copy of that word: every later call of this context fails until sgb_comm_connect* is called again
 
   // ---- state of the last linearize (cached for error(), gicp_factor.hpp:94-96) ----
   bool have_lin = false;

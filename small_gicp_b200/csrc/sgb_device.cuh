@@ -51,11 +51,16 @@ constexpr int kMaxPeers = 8;
 constexpr int kMailStride = 64;
 constexpr size_t kMailFlagOffset = 2 * kMaxPeers * kMailStride * sizeof(double);
 constexpr size_t kMailBytes = kMailFlagOffset + 2 * kMaxPeers * sizeof(unsigned long long);
+constexpr unsigned long long kCommPoison = 1ull << 63;  // flag bit: the sender could not run its reduction (its call failed on the host)
+constexpr int kCommStampRing = 64;                      // wait times of the last 64 exchanges (sgb_comm_wait_ns)
 struct CommParams {
   unsigned char* mail[kMaxPeers];  // mailbox of every rank (mail[rank] is local memory)
   int world, rank;                 // world <= 1: no exchange
   unsigned long long seq;          // sequence number of this call (same on all ranks, > 0)
-  unsigned long long timeout_ns;   // give up waiting for a peer after this long (the result is then NaN)
+  unsigned long long timeout_ns;   // give up waiting for a peer after this long (the result is then NaN and *status becomes non-zero)
+  unsigned int* status;            // sticky device word: 1 = gave up on a peer, 2 = a peer reported a failed call (never cleared by the kernels)
+  unsigned long long* stamps;      // [kCommStampRing]: ns this rank waited for its peers in exchange seq % kCommStampRing (or null)
+  int poison;                      // this rank has nothing valid to contribute: tell the peers (host-side failure after the sequence number was taken)
 };
 
 struct LinParams {
@@ -150,8 +155,9 @@ __device__ __forceinline__ uint32_t kd_nearest(const KdNode* __restrict__ nodes,
 }
 
 /// All-reduce(sum) of one value per thread (threads < NVALS of ONE CTA per rank) over the peer mailboxes -- see CommParams.
-/// Called by ALL threads of the finishing CTA.  A rank whose peers never show up gives up after c.timeout_ns and returns NaN
-/// (a hung collective must not take the GPU down with it).
+/// Called by ALL threads of the finishing CTA.  A rank whose peers never show up gives up after c.timeout_ns, returns NaN and
+/// raises the context's sticky status word, which the host-facing calls turn into a non-zero return code (a hung collective
+/// must not take the GPU down with it, and must not pass for a result either).
 template <int NVALS>
 __device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v) {
   static_assert(NVALS <= kMailStride, "mailbox slot too small");
@@ -163,22 +169,32 @@ __device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v)
   }
   __threadfence_system();
   __syncthreads();
-  __shared__ int s_timeout;
-  if (tid == 0) s_timeout = 0;
+  __shared__ int s_fail;
+  if (tid == 0) {
+    s_fail = 0;
+    if (c.stamps) c.stamps[c.seq % kCommStampRing] = 0ull;
+  }
   __syncthreads();
   if (tid < c.world) {
     __threadfence_system();
     volatile unsigned long long* theirs = reinterpret_cast<volatile unsigned long long*>(c.mail[tid] + kMailFlagOffset) + par * kMaxPeers + c.rank;
-    *theirs = c.seq;  // publish: rank `tid` may now read my slot
+    *theirs = c.poison ? (c.seq | kCommPoison) : c.seq;  // publish: rank `tid` may now read my slot
     volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(c.mail[c.rank] + kMailFlagOffset) + par * kMaxPeers + tid;
-    unsigned long long t0, t1;
+    unsigned long long t0, t1 = 0, f;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*mine != c.seq) {
+    while (((f = *mine) & ~kCommPoison) != c.seq) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > c.timeout_ns) {
-        s_timeout = 1;
+        atomicOr(&s_fail, 1);
         break;
       }
+    }
+    if (f == (c.seq | kCommPoison)) atomicOr(&s_fail, 2);
+    // how long this rank waited for peer `tid` (its own flag is there at once): the slowest peer is the skew + transport,
+    // the rank that arrives last sees the bare transport latency (bench.py: comm_wait_ns, min / max over the ranks)
+    if (c.stamps) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(&c.stamps[c.seq % kCommStampRing], t1 - t0);
     }
   }
   __syncthreads();
@@ -187,8 +203,9 @@ __device__ __forceinline__ double comm_all_reduce(const CommParams& c, double v)
   if (tid < NVALS) {
     const volatile double* slots = reinterpret_cast<const volatile double*>(c.mail[c.rank]) + par * kMaxPeers * kMailStride;
     for (int p = 0; p < c.world; p++) s += slots[p * kMailStride + tid];  // rank order: the same sum on every rank
-    if (s_timeout) s = __longlong_as_double(0x7ff8000000000000ll);
+    if (s_fail) s = __longlong_as_double(0x7ff8000000000000ll);
   }
+  if (tid == 0 && s_fail && c.status) atomicOr(c.status, static_cast<unsigned int>(s_fail));
   return s;
 }
 

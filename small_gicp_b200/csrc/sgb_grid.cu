@@ -126,6 +126,7 @@ __device__ __forceinline__ void grid_scan(const float4* __restrict__ cp, uint32_
   }
 }
 
+#ifdef SGB_PROFILING  // per-cell lists, eight lookups per query (SGB_GRID_BLOCKS=0): superseded by the block lists, kept for A/B runs only
 // ---------------------------------------------------------------------------------------------------------------
 // probe: one query per thread (Hilbert order -> neighbouring lanes hit neighbouring cells)
 // state[i] = 1: settled (corr[i] is the exact nearest neighbour), 0: pending for the tree search (corr[i] = best candidate)
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
     if (pend) pending_list[base + __popc(m & ((1u << lane) - 1u))] = i;
   }
 }
+
+#endif  // SGB_PROFILING
 
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
@@ -552,20 +555,30 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
   // *pending_count must be zero on entry: the previous probe (or the context) cleared it
   const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
-  if (blocks)
-  {
-    static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;  // profiling switch
-    if (batch_tail)
-      grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
-    else if (ctas == 6)
-      grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
-    else if (ctas == 8)
-      grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
-    else
-      grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
-  }
-  else
+#ifdef SGB_PROFILING
+  if (!blocks) {
     grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, next_count);
+    return cudaGetLastError();
+  }
+  static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;
+  if (batch_tail) {
+    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    return cudaGetLastError();
+  }
+  if (ctas == 6) {
+    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    return cudaGetLastError();
+  }
+  if (ctas == 8) {
+    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    return cudaGetLastError();
+  }
+#else
+  (void)blocks;
+  (void)batch_tail;
+  (void)cell;
+#endif
+  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@ namespace sgb {
 // linearize: one thread per source point (grid-stride, Morton-ordered so a warp's queries share
 // their path through the tree), FP32 search on FP32 coordinates, FP64 factor algebra and sums.
 // =============================================================================================
+#ifdef SGB_PROFILING  // single fused kernel (SGB_SEARCH=0): the round-1 starting point, kept for A/B runs only
 template <int FACTOR, int ROBUST>
 __global__ void __launch_bounds__(kLinBlock) linearize_kd_kernel(const __grid_constant__ LinParams P) {
   extern __shared__ uint2 s_stack[];
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(kLinBlock) linearize_kd_kernel(const __grid_co
   }
   block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
 }
+
+#endif  // SGB_PROFILING
 
 // Gaussian-voxel-map target (VGICP): hash probe of 1 / 7 / 27 voxels in the reference's offset order
 // (incremental_voxelmap.hpp:157-186), nearest voxel mean wins, first-found wins ties (knn_result.hpp:81-83).
@@ -221,11 +224,15 @@ static cudaError_t launch_lin(const LinParams& P, bool voxel, int grid, size_t s
     if (FACTOR == 1) return cudaErrorInvalidValue;
     linearize_vox_kernel<(FACTOR == 1 ? 0 : FACTOR), ROBUST><<<grid, kLinBlock, 0, st>>>(P);
   } else {
+#ifdef SGB_PROFILING
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(linearize_kd_kernel<FACTOR, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
     linearize_kd_kernel<FACTOR, ROBUST><<<grid, kLinBlock, smem, st>>>(P);
+#else
+    return cudaErrorNotSupported;  // point targets go through the search + factor kernels (sgb_grid.cu, sgb_kernels_packet.cu, sgb_kernels_split.cu)
+#endif
   }
   return cudaGetLastError();
 }
@@ -273,9 +280,16 @@ cudaError_t launch_reduce_nothing(const LinParams& P, bool linearize, cudaStream
 
 int linearize_occupancy(int stack_depth) {
   int nb = 0;
-  const size_t smem = static_cast<size_t>(stack_depth) * kLinBlock * sizeof(uint2);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(linearize_kd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, linearize_kd_kernel<2, 0>, kLinBlock, smem) != cudaSuccess) return 1;
+#ifdef SGB_PROFILING
+  if (stack_depth > 0) {
+    const size_t smem = static_cast<size_t>(stack_depth) * kLinBlock * sizeof(uint2);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(linearize_kd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, linearize_kd_kernel<2, 0>, kLinBlock, smem) != cudaSuccess) return 1;
+    return nb > 0 ? nb : 1;
+  }
+#endif
+  (void)stack_depth;  // resident CTAs of the voxel-map kernel (VGICP): its grid-stride loop is sized to one wave
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, linearize_vox_kernel<2, 0>, kLinBlock, 0) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
@@ -611,6 +625,17 @@ __global__ void gather_kernel(const uint32_t* __restrict__ perm, size_t n, const
   }
 }
 
+// out[perm[j]] = in[j]: leaf order -> original order (features estimated on the device in leaf order)
+__global__ void scatter_kernel(const uint32_t* __restrict__ perm, size_t n, const float4* __restrict__ in0, float4* out0, const float4* __restrict__ in1,
+                               float4* out1, const float4* __restrict__ in2, float4* out2) {
+  for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < n; j += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t d = perm[j];
+    if (in0) out0[d] = in0[j];
+    if (in1) out1[d] = in1[j];
+    if (in2) out2[d] = in2[j];
+  }
+}
+
 // Morton-rank order -> chunk-transposed order (see LinParams / DevSource::run): out[p] = in[rank(p)]
 __global__ void chunk_transpose_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t K) {
   const size_t chunk_pts = 32ull * K;
@@ -659,6 +684,13 @@ cudaError_t launch_gather(const uint32_t* perm, size_t n, const float4* in0, flo
                           const float4* in3, float4* out3, int sm_count, cudaStream_t st) {
   if (!n) return cudaSuccess;
   gather_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(perm, n, in0, out0, in1, out1, in2, out2, in3, out3);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(const uint32_t* perm, size_t n, const float4* in0, float4* out0, const float4* in1, float4* out1, const float4* in2, float4* out2,
+                           int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  scatter_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(perm, n, in0, out0, in1, out1, in2, out2);
   return cudaGetLastError();
 }
 

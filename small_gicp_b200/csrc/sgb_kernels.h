@@ -11,10 +11,14 @@
 namespace sgb {
 
 /// Launch `kernel` as a programmatic dependent of the previous kernel on `st` (its set-up overlaps the predecessor's tail;
-/// the kernel itself waits with grid_dependency_wait()).  SGB_PDL=0 falls back to plain stream order (A/B switch).
+/// the kernel itself waits with grid_dependency_wait()).  Profiling build: SGB_PDL=0 falls back to plain stream order (A/B switch).
 inline bool pdl_enabled() {
+#ifdef SGB_PROFILING
   static const bool on = !(std::getenv("SGB_PDL") && std::getenv("SGB_PDL")[0] == '0');
   return on;
+#else
+  return true;
+#endif
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
@@ -47,6 +51,8 @@ cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const
                            float4* out_normals, float4* out_covA, float4* out_covB, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);
 cudaError_t launch_gather(const uint32_t* perm, size_t n, const float4* in0, float4* out0, const float4* in1, float4* out1, const float4* in2, float4* out2,
                           const float4* in3, float4* out3, int sm_count, cudaStream_t st);
+cudaError_t launch_scatter(const uint32_t* perm, size_t n, const float4* in0, float4* out0, const float4* in1, float4* out1, const float4* in2, float4* out2,
+                           int sm_count, cudaStream_t st);
 cudaError_t launch_correspondences(const uint32_t* corr, const uint32_t* perm, size_t n, const float4* tgt_pts, int voxel, uint64_t* out, int sm_count,
                                    cudaStream_t st);
 cudaError_t launch_chunk_transpose(const uint32_t* in, uint32_t* out, size_t n, uint32_t K, int sm_count, cudaStream_t st);

@@ -14,6 +14,7 @@
 
 namespace sgb {
 
+#ifdef SGB_PROFILING
 // ---------------------------------------------------------------------------------------------------------------
 // Phase 1.  Every lane owns a run of K consecutive points of the Morton curve (chunk-transposed layout) and walks
 // it INDEPENDENTLY of the other lanes: a lane that finishes a query starts its next one in the same iteration of the
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(kLinBlock) nn_search_kernel(const __grid_const
     }
   }
 }
+
+#endif  // SGB_PROFILING
 
 // ---------------------------------------------------------------------------------------------------------------
 // Phase 2.  One point per thread per tile of kLinBlock points.  The gather of the matched target point / covariance
@@ -261,6 +264,7 @@ int factor_reduce_occupancy(int factor, int robust) {
   }
 }
 
+#ifdef SGB_PROFILING
 int search_occupancy(int stack_depth) {
   int nb = 0;
   const size_t smem = static_cast<size_t>(stack_depth) * kLinBlock * sizeof(uint2);
@@ -278,6 +282,8 @@ cudaError_t launch_search(const LinParams& P, int grid, int stack_depth, cudaStr
   nn_search_kernel<<<grid, kLinBlock, smem, st>>>(P);
   return cudaGetLastError();
 }
+
+#endif  // SGB_PROFILING
 
 cudaError_t launch_factor_reduce(const LinParams& P, int factor, int robust, int grid, cudaStream_t st) {
   switch (factor * 3 + robust) {

@@ -70,11 +70,24 @@ class ShardedReduction:
 class ContextReduction:
     """Adapter: a small_gicp_b200.Context whose source holds this rank's shard; writes straight into device memory."""
 
-    def __init__(self, ctx, factor, robust=0, robust_c=1.0, rejector=1, max_dist_sq=1.0):
-        self.ctx, self.kw = ctx, dict(factor=factor, robust=robust, robust_c=robust_c, rejector=rejector, max_dist_sq=max_dist_sq)
+    def __init__(self, ctx, factor, robust=0, robust_c=1.0, rejector=1, max_dist_sq=1.0, bind_stream=True):
+        """bind_stream: run the context on torch's CURRENT stream (the one ShardedReduction's all_reduce / .cpu() are ordered on).
+        A context keeps its own non-blocking stream otherwise, and nothing would order the collective after the kernel."""
+        import torch
 
-    def linearize_into(self, T, buf):
-        self.ctx.linearize_device(T, buf.data_ptr(), **self.kw)
+        self.ctx, self.kw = ctx, dict(factor=factor, robust=robust, robust_c=robust_c, rejector=rejector, max_dist_sq=max_dist_sq)
+        self.bound = bool(bind_stream) and torch.cuda.is_available()
+        if self.bound:
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def _order(self):
+        if not self.bound:  # the context runs on a stream torch knows nothing about: finish its work before torch touches the buffer
+            self.ctx.synchronize()
+
+    def linearize_into(self, T, buf, **kw):
+        self.ctx.linearize_device(T, buf.data_ptr(), **dict(self.kw, **kw))
+        self._order()
 
     def error_into(self, T, buf1):
         self.ctx.error_device(T, buf1.data_ptr())
+        self._order()

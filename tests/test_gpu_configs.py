@@ -106,7 +106,11 @@ def test_size_sweep_first_and_converged_pose(n, factor):
     for T in (np.eye(4), Tgt):  # iteration-0 pose and converged pose (traversal cost differs, sums must not)
         H0, b0, e0 = reg.linearize(tc, tt, sc, T)
         H, b, e = ctx.linearize(T, factor=factor)
-        nm = NF.compare_correspondences(ctx.correspondences(), reg.correspondences(len(sc)), tc.points, sc.points, T)
+        cg = ctx.correspondences()
+        nm = NF.compare_correspondences(cg, reg.correspondences(len(sc)), tc.points, sc.points, T)
+        # always: the GPU sums against numpy over the GPU's own correspondences; when the sets agree also against the oracle
+        Hn, bn, en = NF.linearize(T, cg, factor, 0, 1.0, sc.points, sc.covs, tc.points, tc.normals, tc.covs)
+        assert np.linalg.norm(H - Hn) <= 2e-5 * np.linalg.norm(Hn) and abs(e - en) <= 2e-5 * en
         if nm == 0:
             assert np.linalg.norm(H - H0) <= 2e-5 * np.linalg.norm(H0) and abs(e - e0) <= 2e-5 * e0
     ctx.close()

@@ -107,12 +107,60 @@ def test_missing_peer_times_out_instead_of_hanging(monkeypatch):
     sg = _sg()
     tgt, tcov, src, scov, T = _pair(20_000)
     n = src.shape[0]
-    monkeypatch.setenv("SGB_COMM_TIMEOUT_MS", "300")
     ctxs = _contexts(2, tgt, tcov, src, scov, [(0, n // 2), (n // 2, n)])
+    ctxs[0].comm_set_timeout_ms(300)
     out = torch.zeros(64, dtype=torch.float64, device="cuda")
     ctxs[0].linearize_device(T, out.data_ptr())  # rank 1 never calls
     ctxs[0].synchronize()
     assert np.isnan(out.cpu().numpy()[:44]).all()
+    assert ctxs[0].comm_status() & 1  # ... and it is not a silent NaN: the sticky status word says "timeout"
+    with pytest.raises(sg.SgbError):  # the context refuses further collective work until it is reconnected
+        ctxs[0].linearize(T)
+    for c in ctxs:
+        c.close()
+
+
+def test_host_call_reports_peer_timeout_as_error():
+    """sgb_linearize (host-returning) turns a timed-out exchange into a non-zero return code instead of NaN sums with rc == 0."""
+    sg = _sg()
+    tgt, tcov, src, scov, T = _pair(20_000)
+    n = src.shape[0]
+    ctxs = _contexts(2, tgt, tcov, src, scov, [(0, n // 2), (n // 2, n)])
+    ctxs[0].comm_set_timeout_ms(200)
+    with pytest.raises(sg.SgbError, match="peer"):
+        ctxs[0].linearize(T)
+    for c in ctxs:
+        c.close()
+
+
+def test_failed_call_on_one_rank_tells_the_peers():
+    """A call that fails on the HOST of one rank (here: GICP without source covariances) still takes its sequence number and tells the
+    peers: they get an error at once (status bit 1), not a 5 s timeout, and after a re-connect the group works again."""
+    import time
+
+    import torch
+
+    sg = _sg()
+    tgt, tcov, src, scov, T = _pair(20_000)
+    n = src.shape[0]
+    ctxs = _contexts(2, tgt, tcov, src, scov, [(0, n // 2), (n // 2, n)])
+    ctxs[1].set_source(src[n // 2 :], None)  # rank 1 loses its covariances: its GICP linearize fails validation
+    out = torch.zeros(64, dtype=torch.float64, device="cuda")
+    with pytest.raises(sg.SgbError):
+        ctxs[1].linearize_device(T, out.data_ptr())
+    t0 = time.perf_counter()
+    with pytest.raises(sg.SgbError, match="peer"):
+        ctxs[0].linearize(T)
+    assert time.perf_counter() - t0 < 2.0  # far below the 5 s timeout: the peer said so
+    assert ctxs[0].comm_status() & 2
+    # re-connect and carry on
+    ctxs[1].set_source(src[n // 2 :], scov[n // 2 :])
+    boxes = [c.comm_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.comm_connect_ptrs(r, 2, boxes)
+    ctxs[1].linearize_device(T, out.data_ptr())
+    H, b, e = ctxs[0].linearize(T)
+    assert np.isfinite(H).all() and e > 0
     for c in ctxs:
         c.close()
 
@@ -214,3 +262,38 @@ def test_sharded_vgicp_lm_matches_unsharded_and_oracle(world):
     assert rot < 5e-3 and trans < 5e-2
     for c in ctxs + [full]:
         c.close()
+
+
+@pytest.mark.parametrize("bind", [True, False])
+def test_context_reduction_is_ordered_with_torch(bind):
+    """distributed.ContextReduction: the context's kernels and torch's read of the result buffer must be ordered -- either the
+    context runs on torch's current stream (bind_stream=True) or the adapter synchronises the context before torch looks.
+    Keyword overrides of linearize() reach the kernel."""
+    import torch
+
+    from small_gicp_b200.distributed import ContextReduction, ShardedReduction
+
+    sg = _sg()
+    tgt, tcov, src, scov, T = _pair(40_000)
+    ref = sg.Context(0)
+    ref.set_target(tgt, None, tcov)
+    ref.build_target_kdtree(0)
+    ref.set_source(src, scov)
+    ctx = sg.Context(0)
+    ctx.set_target(tgt, None, tcov)
+    ctx.build_target_kdtree(0)
+    ctx.set_source(src, scov)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        red = ShardedReduction(ContextReduction(ctx, sg.FACTOR_GICP, bind_stream=bind), device="cuda")
+        for _ in range(20):  # a race would show up as a stale / zero buffer in some repetition
+            for pose in (np.eye(4), T):
+                H0, b0, e0 = ref.linearize(pose)
+                H, b, e, ninl = red.linearize(pose)
+                assert np.array_equal(H, H0) and e == e0 and ninl == ref.num_inliers()
+                assert red.error(pose) == ref.error(pose)
+        H0, b0, e0 = ref.linearize(T, max_dist_sq=0.01)
+        H, b, e, _ = red.linearize(T, max_dist_sq=0.01)
+        assert np.array_equal(H, H0) and e == e0
+    ctx.close()
+    ref.close()

@@ -32,9 +32,9 @@ def _sg():
     return sg
 
 
-def load_ctx(target, tree, source, own_tree=False):
+def load_ctx(target, tree, source, own_tree=False, profiling=False):
     sg = _sg()
-    ctx = sg.Context(0)
+    ctx = sg.Context(0, profiling=profiling)
     ctx.set_target(target.points, target.normals, target.covs)
     if own_tree:
         ctx.build_target_kdtree(0)
@@ -200,13 +200,21 @@ def test_voxelmap_target(golden_prepared):
             cpu = reg.linearize(vm, None, g["source"], T)
             gpu = ctx.linearize(T, factor=sg.FACTOR_GICP)
             c = reg.correspondences(len(g["source"]))
-            nm = int((ctx.correspondences() != c).sum())
+            cg = ctx.correspondences()
+            nm = int((cg != c).sum())
             assert nm <= 2
+            # GPU sums against the numpy leg over the GPU's OWN correspondences (always), and against the oracle when they agree
+            src = g["source"]
+            vox_id = np.where(cg == sg.NO_CORRESPONDENCE, NF.NO, cg >> np.uint64(32))  # calc_index: voxel id << 32 (incremental_voxelmap.hpp:151)
+            args = (2, 0, 1.0, src.points, src.covs, means, None, covs)
+            check_linearized(gpu, NF.linearize(T, vox_id, *args), ("vgicp-numpy", offsets))
+            T2 = T @ O.se3_exp(np.array([0.01, 0.0, -0.01, 0.02, 0.02, 0.0]))
+            e_gpu = ctx.error(T2)
+            e_npy = NF.error(T2, T, vox_id, *args)
+            assert abs(e_gpu - e_npy) <= RTOL * e_npy
             if nm == 0:
                 check_linearized(gpu, cpu, ("vgicp", offsets))
-                T2 = T @ O.se3_exp(np.array([0.01, 0.0, -0.01, 0.02, 0.02, 0.0]))
-                e_cpu, e_gpu = reg.error(vm, g["source"], T2), ctx.error(T2)
-                assert abs(e_gpu - e_cpu) <= RTOL * e_cpu
+                assert abs(e_gpu - reg.error(vm, g["source"], T2)) <= RTOL * e_npy
         ctx.close()
 
 
@@ -361,8 +369,16 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        ctx = load_ctx(tc, tt, sc, own_tree=own)
+        ctx = load_ctx(tc, tt, sc, own_tree=own, profiling=True)  # the SGB_* switches only exist in libsgicp_b200_prof.so
         ctx.linearize(np.eye(4))  # also exercises the seeded second search
+        H, b, e = ctx.linearize(Tgt)
+        results[name] = (H, b, e, ctx.correspondences())
+        ctx.close()
+    for k in switches:
+        monkeypatch.delenv(k, raising=False)
+    for name, own in (("product/device-kd", True), ("product/reference-kd", False)):  # the shipped library (no switches) against all of them
+        ctx = load_ctx(tc, tt, sc, own_tree=own)
+        ctx.linearize(np.eye(4))
         H, b, e = ctx.linearize(Tgt)
         results[name] = (H, b, e, ctx.correspondences())
         ctx.close()
@@ -394,7 +410,7 @@ def test_grid_far_and_unbounded_queries(synthetic_pair, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        ctx = load_ctx(tc, tt, sc, own_tree=True)
+        ctx = load_ctx(tc, tt, sc, own_tree=True, profiling=bool(env))  # "grid" = the product library, the variants need the switches
         res = []
         for T, rej, md in cases:
             H, b, e = ctx.linearize(T, factor=sg.FACTOR_GICP, rejector=rej, max_dist_sq=md)

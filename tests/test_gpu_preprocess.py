@@ -151,3 +151,62 @@ def test_batch_knn_matches_oracle(golden, k):
     idx, d2 = c.target_batch_knn(queries[:10], 5)
     c.close()
     assert np.all(idx[:, 3:] == np.uint64(0xFFFFFFFFFFFFFFFF)) and np.all(idx[:, :3] < 3)
+
+
+def test_source_features_survive_a_voxelmap_build(golden):
+    """The VGICP order of calls: set_source -> build_target_voxelmap -> estimate_source_features.  The voxel-map build used to
+    scribble its integer voxel coordinates over the buffer that holds the source in original order; the source covariances
+    then came out of garbage.  They must equal those estimated before the map was built."""
+    import small_gicp_b200 as sg
+
+    tgt, src, T = golden
+    a, b = sg.Context(0), sg.Context(0)
+    tp = a.voxelgrid_sampling(tgt, 0.25)
+    sp = a.voxelgrid_sampling(src, 0.25)
+    _, tcov = a.estimate_features(tp, 10, normals=False)
+    a.set_source(sp)
+    a.build_target_voxelmap(tp, tcov, 1.0)
+    a.estimate_source_features(10)
+    b.set_source(sp)
+    b.estimate_source_features(10)
+    b.build_target_voxelmap(tp, tcov, 1.0)
+    Ha, ba, ea = a.linearize(T, factor=sg.FACTOR_GICP)
+    Hb, bb, eb = b.linearize(T, factor=sg.FACTOR_GICP)
+    assert np.array_equal(Ha, Hb) and ea == eb and ea > 0
+    # and against covariances that made the round trip through the host
+    _, scov = b.estimate_features(sp, 10, normals=False)
+    b.set_source(sp, scov)
+    Hc, bc, ec = b.linearize(T, factor=sg.FACTOR_GICP)
+    assert np.linalg.norm(Ha - Hc) <= 1e-4 * np.linalg.norm(Hc)
+    with pytest.raises(sg.SgbError):  # no source at all: refused, not computed from whatever the scratch buffer holds
+        c = sg.Context(0)
+        c.estimate_source_features(10)
+    a.close()
+    b.close()
+
+
+def test_device_features_follow_a_tree_rebuild(golden):
+    """Features estimated on the device live in leaf order; re-building (or adopting another) tree re-permutes the points.  The
+    features must follow their points: same sums before and after the rebuild, for either tree."""
+    import small_gicp_b200 as sg
+
+    tgt, src, T = golden
+    a = sg.Context(0)
+    tp = a.voxelgrid_sampling(tgt, 0.25)
+    sp = a.voxelgrid_sampling(src, 0.25)
+    a.set_target(tp)
+    a.build_target_kdtree()
+    a.estimate_target_features(10)
+    a.set_source(sp)
+    a.estimate_source_features(10)
+    ref = {f: a.linearize(T, factor=f) for f in (sg.FACTOR_GICP, sg.FACTOR_PLANE_ICP)}
+    tree = O.KdTree(O.Cloud(tp))
+    a.set_target_kdtree(*tree.export())  # a different permutation of the same points
+    for f, (H0, b0, e0) in ref.items():
+        H, b, e = a.linearize(T, factor=f)
+        assert np.linalg.norm(H - H0) <= 1e-6 * np.linalg.norm(H0) and abs(e - e0) <= 1e-6 * e0, f
+    a.build_target_kdtree()
+    for f, (H0, b0, e0) in ref.items():
+        H, b, e = a.linearize(T, factor=f)
+        assert np.linalg.norm(H - H0) <= 1e-6 * np.linalg.norm(H0) and abs(e - e0) <= 1e-6 * e0, f
+    a.close()
