@@ -1,34 +1,3 @@
-# INTEGRATION — adding the B200 backend to koide3/small_gicp
-
-The backend is a **Reduction** type, the reference's own extension point for this path
-(`include/small_gicp/registration/reduction.hpp:12-63`, `reduction_omp.hpp:20-73`, `reduction_tbb.hpp:114-139`).
-`Registration<PointFactor, Reduction, …>::align` (`registration/registration.hpp:31-43`) and both optimizers
-(`registration/optimizer.hpp:42,102,113`) call exactly two member templates of it:
-
-```cpp
-std::tuple<Eigen::Matrix<double,6,6>, Eigen::Matrix<double,6,1>, double>
-linearize(const Target&, const Source&, const TargetTree&, const Rejector&, const Eigen::Isometry3d& T, std::vector<Factor>&) const;
-double error(const Target&, const Source&, const Eigen::Isometry3d& T, std::vector<Factor>&) const;
-```
-
-Everything per-point behind those two calls runs in `libsgicp_b200.so` through the C-ABI declared in
-[`include/sgicp_b200.h`](include/sgicp_b200.h) (plain pointers and sizes; no Eigen, torch or CUDA types in any signature).
-
-## 1. What a maintainer adds to the reference tree
-
-One header, [`include/small_gicp/registration/reduction_cuda.hpp`](include/small_gicp/registration/reduction_cuda.hpp), plus
-`target_link_libraries(... sgicp_b200)`.  The file below is not a sketch: `tests/host_ref/Makefile` compiles exactly this file with
-`-I/root/reference/include` (the reference's headers in place, nothing copied; Eigen is absent from the build image, so both it and the
-reference compile against the Eigen API shim of `oracle/ref_build/eigen_shim`), instantiates the **reference's own**
-`Registration<ICPFactor | PointToPlaneICPFactor | GICPFactor | RobustFactor<Huber|Cauchy, ·>, ParallelReductionCUDA, NullFactor,
-NullRejector | DistanceRejector, GaussNewtonOptimizer | LevenbergMarquardtOptimizer>` next to the same template on `ParallelReductionOMP`,
-and `tests/test_host_ref_dropin.py` compares the two `RegistrationResult`s on the GPU (pose within 1e-4 rad / 1e-3 m, same `iterations`,
-`num_inliers` ± 2) and checks that this document shows the compiled file verbatim (`scripts/sync_integration_md.py` refreshes the block).
-This repository's own Eigen-free mirror of the template surface (`small_gicp_b200/host/include/small_gicp_b200/`, namespace
-`small_gicp_b200`) carries the same reduction for users without the reference tree.
-
-<!-- BEGIN reduction_cuda.hpp -->
-```cpp
 // SPDX-License-Identifier: MIT
 // include/small_gicp/registration/reduction_cuda.hpp -- the ONE header a maintainer adds to koide3/small_gicp to get the B200
 // backend (plus `target_link_libraries(... sgicp_b200)`).  It is written against the reference's own types and compiled,
@@ -345,63 +314,3 @@ private:
 };
 
 }  // namespace small_gicp
-```
-<!-- END reduction_cuda.hpp -->
-
-Use: `Registration<GICPFactor, ParallelReductionCUDA> reg; reg.align(target, source, target_tree, init_T);` — nothing else in the
-reference changes.  `registration_helper.cpp:88-115` would gain one more `case`/setting that instantiates this reduction.
-
-## 2. The `factors` contract
-
-After `linearize`, `factors[i].inlier()` must tell whether point *i* was accepted (`optimizer.hpp:60,146` count them) and a following
-`error()` must use the same correspondences and, for GICP, the same fused precision matrix (`gicp_factor.hpp:81-89`).
-
-* The correspondences and the linearisation pose stay **on the device** (`sgb_error` re-derives the precision matrix from that pose,
-  bit-identically to `sgb_linearize`); `GICPFactor::mahalanobis` is never shipped back.
-* Conservative mode (`sync_every_linearize = true`, the default: the stock optimizers work unchanged): copy `target_index` back after
-  every `linearize` — one 8 B/point D2H + a host loop.
-* Fast mode (`sync_every_linearize = false`; what this repository's own `Registration<>` mirror does,
-  `small_gicp_b200/host/include/small_gicp_b200/registration.hpp`): the optimizers call `reduction.sync_factors(factors)` **once**, after
-  the last iteration, if the reduction provides it (detected with `std::void_t`).  In the reference that is a 4-line change in
-  `optimizer.hpp` before the two `count_if`s; without it `num_inliers` reads 0 in this mode (`test_single_sync_mode`).
-
-## 3. Ownership, errors, threading
-
-| Aspect | Convention |
-|---|---|
-| Inputs | borrowed for the duration of each `sgb_*` call only; the context owns all device memory.  Clouds handed over in page-locked host memory are copied asynchronously (CUDA's rule): leave them unchanged until `sgb_synchronize` or the next call that returns results to the host |
-| Mirrors | target, search structure and source are uploaded at the FIRST `linearize()` of every `align()` (recognised by the freshly constructed factor vector of `registration.hpp:41`) and re-used for the remaining iterations of that `align()`.  A cloud that really stays the same over many `align()` calls is kept across them when the caller sets a non-zero `target_generation` / `source_generation` (and bumps it on every edit); `invalidate()` forgets everything.  No content sampling: an in-place edit between two `align()` calls is always seen (`test_source_edited_in_place_between_aligns`) |
-| Errors | every `sgb_*` returns 0 or an error code, message via `sgb_last_error`; the glue turns them into `std::runtime_error` (the reference itself only warns on `std::cerr` or aborts on this path, `registration.hpp:34-39`, `registration_helper.cpp:84-86`) |
-| Empty clouds | `linearize` over an empty source or target returns zeros (`helper_test.cpp:53-59`) |
-| No device | `sgb_create` fails with a message; there is **no CPU fallback** |
-| Threading | one context per reduction object, one CUDA stream per context; a context is not thread-safe, distinct contexts are (TBB flow-graph users give each node its own `Registration` object) |
-| `num_threads` | kept as an ignored public field so code that sets `reg.reduction.num_threads` still compiles |
-
-## 4. Python / other FFI
-
-`small_gicp_b200/capi.py` is the ctypes binding of the same C-ABI (numpy in, numpy out) — the stub a `pybind11` maintainer would
-replace `src/python/align.cpp:245-253` with.  No other language toolchain from the reference is involved (it is C++ + pybind11 only).
-
-## 5. More than one GPU
-
-The reference has no multi-device path (its reductions sum inside one process: `reduction_omp.hpp:24-58`, `reduction_tbb.hpp:70-92`), so this is an
-addition, not a replacement.  One process per GPU; every rank holds the whole target and a contiguous shard of the source.  After the ranks have
-exchanged their 64-byte mailbox handles once, the glue above works unchanged: `linearize` / `error` return the sum over all ranks, because the
-CTA that finishes the reduction kernel exchanges its sums with the peers' mailboxes over NVLink before it writes `H|b|e`.
-
-```cpp
-// per rank, after sgb_create():                      any transport gathers the handles -- MPI, a file, torch.distributed ...
-unsigned char mine[SGB_COMM_HANDLE_BYTES], all[SGB_COMM_MAX_RANKS * SGB_COMM_HANDLE_BYTES];
-check(sgb_comm_handle(ctx, mine));
-MPI_Allgather(mine, SGB_COMM_HANDLE_BYTES, MPI_BYTE, all, SGB_COMM_HANDLE_BYTES, MPI_BYTE, MPI_COMM_WORLD);
-check(sgb_comm_connect(ctx, rank, world, all));
-MPI_Barrier(MPI_COMM_WORLD);                          // every mailbox is mapped and cleared before the first exchange
-// ... sgb_source_set_points(ctx, shard_size, shard_points, shard_covs); Registration::align as before; all ranks step in lockstep
-```
-
-Python: `small_gicp_b200.distributed.connect_fused(ctx)` does the same over `torch.distributed`; `bench.py --gpus N` uses it.
-All ranks must issue the same sequence of `linearize` / `error` calls (as with any collective).  A peer that never shows up makes the waiting
-rank give up after 5 s (`sgb_comm_set_timeout_ms`): `sgb_linearize` / `sgb_error` then **return a non-zero code** (the glue throws), the sums are NaN, and the
-context refuses further collective work until `sgb_comm_connect` is called again.  A call that fails on the host of one rank (bad argument, missing
-covariances) still takes part in the exchange and tells its peers, so they fail at once instead of waiting for the timeout; users of the `*_device`
-variants read `sgb_comm_status`.

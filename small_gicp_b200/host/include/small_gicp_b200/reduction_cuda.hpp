@@ -10,6 +10,7 @@
 // argument types are compile errors, never a CPU fallback.
 #pragma once
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -26,40 +27,16 @@ namespace small_gicp_b200 {
 
 namespace detail {
 
-/// Identity of a host object as far as the device mirror is concerned: address, element count and a
-/// fingerprint of a strided sample of its bytes (catches re-use of a freed address by a different cloud).
+/// Identity of a host object as far as its device mirror is concerned.  No content sampling: a cloud edited in place between two
+/// align() calls is re-uploaded because every align() re-validates its mirrors (see ParallelReductionCUDA), not because a hash of a
+/// few points happened to change.
 struct MirrorKey {
   const void* addr = nullptr;
   size_t count = 0;
-  uint64_t fingerprint = 0;
-  bool operator==(const MirrorKey& o) const { return addr == o.addr && count == o.count && fingerprint == o.fingerprint; }
+  uint64_t generation = 0;
+  bool operator==(const MirrorKey& o) const { return addr == o.addr && count == o.count && generation == o.generation; }
   bool operator!=(const MirrorKey& o) const { return !(*this == o); }
 };
-
-inline uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
-  const unsigned char* p = static_cast<const unsigned char*>(data);
-  for (size_t i = 0; i < bytes; i++) h = (h ^ p[i]) * 1099511628211ull;
-  return h;
-}
-
-template <typename Cloud>
-MirrorKey cloud_key(const Cloud& cloud) {
-  MirrorKey k;
-  k.addr = &cloud;
-  k.count = traits::size(cloud);
-  uint64_t h = 1469598103934665603ull;
-  const size_t n = k.count, step = n > 64 ? n / 64 : 1;
-  for (size_t i = 0; i < n; i += step) {
-    const Vector4d p = traits::point(cloud, i);
-    h = fnv1a(p.data(), sizeof(double) * 3, h);
-    if (traits::has_covs(cloud)) {
-      const Matrix4d c = traits::cov(cloud, i);
-      h = fnv1a(c.data(), sizeof(double) * 3, h);
-    }
-  }
-  k.fingerprint = h;
-  return k;
-}
 
 /// Contiguous views of a cloud in the C-ABI's layout (N x 4 / N x 16 doubles).  PointCloud is passed
 /// through without a copy; any other cloud type is gathered through its traits.
@@ -100,6 +77,7 @@ struct CloudArrays {
 struct DeviceMirror {
   sgb_ctx* ctx = nullptr;
   MirrorKey target_key, tree_key, source_key;
+  bool target_valid = false, source_valid = false;
   ~DeviceMirror() {
     if (ctx) sgb_destroy(ctx);
   }
@@ -110,17 +88,23 @@ struct dependent_false : std::false_type {};
 
 }  // namespace detail
 
+/// When are the clouds (re)uploaded?  At the FIRST linearize() of every align() -- recognised by the freshly constructed factor vector
+/// Registration::align hands in -- and the mirror is re-used for the remaining iterations of that align().  A cloud that stays the same
+/// over many align() calls is kept across them when the caller sets a non-zero target_generation / source_generation (and bumps it on
+/// every edit).  Same policy, same field names as include/small_gicp/registration/reduction_cuda.hpp (the Eigen-typed twin).
 struct ParallelReductionCUDA {
-  ParallelReductionCUDA() : device(0), num_threads(0) {}
+  ParallelReductionCUDA() : device(0), num_threads(0), target_generation(0), source_generation(0) {}
 
   /// Sum of the linearised per-point factors: (H 6x6, b 6x1, e).
   template <typename TargetPointCloud, typename SourcePointCloud, typename TargetTree, typename CorrespondenceRejector, typename Factor>
   std::tuple<Matrix6d, Vector6d, double> linearize(const TargetPointCloud& target, const SourcePointCloud& source, const TargetTree& target_tree,
                                                    const CorrespondenceRejector& rejector, const Isometry3d& T, std::vector<Factor>& factors) const {
     sgb_ctx* ctx = context();
-    mirror_target(ctx, target, target_tree);
-    mirror_source(ctx, source);
     if (factors.size() != traits::size(source)) throw std::runtime_error("ParallelReductionCUDA: factors.size() != size(source)");
+    // a factor vector nobody has linearized yet = first iteration of an align(): the mirrors are re-validated
+    const bool fresh = factors.empty() || factor_traits<Factor>::state(factors[0]).source_index == std::numeric_limits<size_t>::max();
+    mirror_target(ctx, target, target_tree, fresh);
+    mirror_source(ctx, source, fresh);
     const FactorDescriptor fd = factor_traits<Factor>::describe(factors.empty() ? Factor() : factors[0]);
     double out[43];
     check(ctx, sgb_linearize(ctx, fd.factor_kind, fd.robust_kind, fd.robust_c, CorrespondenceRejector::kind, rejector.threshold(), T.data(), out));
@@ -128,6 +112,7 @@ struct ParallelReductionCUDA {
     Vector6d b;
     std::memcpy(H.data(), out, sizeof(double) * 36);  // symmetric: row/col-major agree
     std::memcpy(b.data(), out + 36, sizeof(double) * 6);
+    if (!factors.empty()) factor_traits<Factor>::state(factors[0]).source_index = 0;  // "this vector has been linearized" (see `fresh`)
     return {H, b, out[42]};
   }
 
@@ -164,7 +149,7 @@ struct ParallelReductionCUDA {
 
   /// Forget the device copies (call after mutating a cloud in place between align() calls).
   void invalidate() const {
-    if (mirror) mirror->target_key = mirror->tree_key = mirror->source_key = detail::MirrorKey();
+    if (mirror) mirror->target_valid = mirror->source_valid = false;
   }
 
   sgb_ctx* context() const {
@@ -175,65 +160,84 @@ struct ParallelReductionCUDA {
     return mirror->ctx;
   }
 
-  int device;       ///< CUDA device ordinal
-  int num_threads;  ///< accepted for source compatibility with the OMP / TBB reductions; unused
+  int device;                  ///< CUDA device ordinal
+  int num_threads;             ///< accepted for source compatibility with the OMP / TBB reductions; unused
+  uint64_t target_generation;  ///< non-zero: keep the target mirror across align() calls while (address, size, generation) match
+  uint64_t source_generation;  ///< same for the source
 
 private:
   static void check(sgb_ctx* ctx, int rc) {
     if (rc != 0) throw std::runtime_error(std::string("ParallelReductionCUDA: ") + sgb_last_error(ctx));
   }
 
+  bool reusable(const detail::MirrorKey& have, const detail::MirrorKey& want, bool valid, bool fresh) const {
+    if (!valid || have != want) return false;
+    return !fresh || want.generation != 0;  // a new align() re-uploads unless the caller vouches for the cloud with a generation
+  }
+  template <typename Cloud>
+  detail::MirrorKey cloud_key(const Cloud& cloud, uint64_t generation) const {
+    detail::MirrorKey k;
+    k.addr = &cloud;
+    k.count = traits::size(cloud);
+    k.generation = generation;
+    return k;
+  }
+
   template <typename Source>
-  void mirror_source(sgb_ctx* ctx, const Source& source) const {
-    const detail::MirrorKey key = detail::cloud_key(source);
-    if (key == mirror->source_key) return;
+  void mirror_source(sgb_ctx* ctx, const Source& source, bool fresh) const {
+    const detail::MirrorKey key = cloud_key(source, source_generation);
+    if (reusable(mirror->source_key, key, mirror->source_valid, fresh)) return;
     detail::CloudArrays<Source> a(source, false);
     check(ctx, sgb_source_set_points(ctx, a.n, a.points, a.covs));
     mirror->source_key = key;
+    mirror->source_valid = true;
   }
 
   // ---- target + search structure ----
   template <typename Target, typename Cloud, typename Projection>
-  void mirror_target(sgb_ctx* ctx, const Target& target, const KdTree<Cloud, Projection>& tree) const {
-    mirror_target(ctx, target, tree.kdtree);
+  void mirror_target(sgb_ctx* ctx, const Target& target, const KdTree<Cloud, Projection>& tree, bool fresh) const {
+    mirror_target(ctx, target, tree.kdtree, fresh);
   }
   template <typename Target, typename Cloud, typename Projection>
-  void mirror_target(sgb_ctx* ctx, const Target& target, const UnsafeKdTree<Cloud, Projection>& tree) const {
+  void mirror_target(sgb_ctx* ctx, const Target& target, const UnsafeKdTree<Cloud, Projection>& tree, bool fresh) const {
     static_assert(std::is_same_v<Projection, AxisAlignedProjection>, "the device search supports axis-aligned kd-trees");
-    const detail::MirrorKey key = detail::cloud_key(target);
+    const detail::MirrorKey key = cloud_key(target, target_generation);
     detail::MirrorKey tkey;
     tkey.addr = &tree;
     tkey.count = tree.nodes.size();
-    tkey.fingerprint = tree.nodes.empty() ? 0 : detail::fnv1a(tree.nodes.data(), std::min<size_t>(tree.nodes.size(), 64) * sizeof(KdTreeNode));
-    if (key == mirror->target_key && tkey == mirror->tree_key) return;
+    tkey.generation = target_generation;
+    if (reusable(mirror->target_key, key, mirror->target_valid, fresh) && tkey == mirror->tree_key) return;
     detail::CloudArrays<Target> a(target, true);
     check(ctx, sgb_target_set_points(ctx, a.n, a.points, a.normals, a.covs));
     static_assert(sizeof(size_t) == sizeof(uint64_t), "64-bit size_t expected");
     check(ctx, sgb_target_set_kdtree(ctx, tree.nodes.data(), tree.nodes.size(), tree.root, reinterpret_cast<const uint64_t*>(tree.indices.data())));
     mirror->target_key = key;
     mirror->tree_key = tkey;
+    mirror->target_valid = true;
   }
   template <typename Target, typename Cloud>
-  void mirror_target(sgb_ctx* ctx, const Target& target, const DeviceKdTree<Cloud>& tree) const {
-    const detail::MirrorKey key = detail::cloud_key(target);
+  void mirror_target(sgb_ctx* ctx, const Target& target, const DeviceKdTree<Cloud>& tree, bool fresh) const {
+    const detail::MirrorKey key = cloud_key(target, target_generation);
     detail::MirrorKey tkey;
     tkey.addr = &tree;
     tkey.count = static_cast<size_t>(tree.max_leaf_size);
-    if (key == mirror->target_key && tkey == mirror->tree_key) return;
+    tkey.generation = target_generation;
+    if (reusable(mirror->target_key, key, mirror->target_valid, fresh) && tkey == mirror->tree_key) return;
     detail::CloudArrays<Target> a(target, true);
     check(ctx, sgb_target_set_points(ctx, a.n, a.points, a.normals, a.covs));
     check(ctx, sgb_target_build_kdtree(ctx, tree.max_leaf_size));
     mirror->target_key = key;
     mirror->tree_key = tkey;
+    mirror->target_valid = true;
   }
   /// VGICP: the voxel map is both the target "cloud" and the search structure.
-  void mirror_target(sgb_ctx* ctx, const GaussianVoxelMap& target, const GaussianVoxelMap& tree) const {
+  void mirror_target(sgb_ctx* ctx, const GaussianVoxelMap& target, const GaussianVoxelMap& tree, bool fresh) const {
     if (&target != &tree) throw std::runtime_error("ParallelReductionCUDA: a voxel-map target must also be passed as the target tree");
     detail::MirrorKey key;
     key.addr = &target;
     key.count = target.size();
-    key.fingerprint = target.generation * 1315423911ull + target.search_offsets.size();
-    if (key == mirror->target_key && key == mirror->tree_key) return;
+    key.generation = target_generation ? target_generation * 1315423911ull + target.generation : 0;  // the map counts its own inserts
+    if (reusable(mirror->target_key, key, mirror->target_valid, fresh) && key == mirror->tree_key) return;
     const size_t n = target.size();
     std::vector<int32_t> coords(n * 3);
     std::vector<Vector4d> means(n);
@@ -249,6 +253,7 @@ private:
     check(ctx, sgb_target_set_voxelmap(ctx, target.leaf_size, n, coords.data(), n ? means[0].data() : nullptr, n ? covs[0].data() : nullptr,
                                        static_cast<int>(target.search_offsets.size())));
     mirror->target_key = mirror->tree_key = key;
+    mirror->target_valid = true;
   }
 
   mutable std::shared_ptr<detail::DeviceMirror> mirror;

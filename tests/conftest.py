@@ -19,6 +19,7 @@ def pytest_sessionstart(session):
     something is MISSING -- on the GPU box the libraries arrive pre-built with the snapshot and must not be rebuilt because of clock skew."""
     needed = [
         os.path.join(ROOT, "small_gicp_b200", "lib", "libsgicp_b200.so"),
+        os.path.join(ROOT, "small_gicp_b200", "lib", "libsgicp_b200_prof.so"),
         os.path.join(ROOT, "small_gicp_b200", "lib", "libsgicp_b200_host.so"),
         os.path.join(ROOT, "oracle", "libsgicp_oracle.so"),
     ]
