@@ -91,12 +91,27 @@ def _lib(profiling=False):
     return _LIBS[profiling]
 
 
+def _is_dev(a):
+    """a torch tensor (host or CUDA): passed by address -- the library copies with cudaMemcpyDefault, so device-resident producers
+    hand their buffers over without a host round trip"""
+    return hasattr(a, "data_ptr") and hasattr(a, "is_contiguous")
+
+
 def _f64(a):
+    if _is_dev(a):
+        import torch
+
+        assert a.dtype == torch.float64 and a.is_contiguous(), "torch inputs must be contiguous float64"
+        return a
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
 def _d(a):
-    return None if a is None else a.ctypes.data_as(_dp)
+    if a is None:
+        return None
+    if _is_dev(a):
+        return C.cast(C.c_void_p(a.data_ptr()), _dp)
+    return a.ctypes.data_as(_dp)
 
 
 def _pose(T):
@@ -106,6 +121,9 @@ def _pose(T):
 
 
 def _points4(p):
+    if _is_dev(p):
+        assert p.dim() == 2 and p.shape[1] == 4, "torch point inputs must be (N, 4) = (x, y, z, 1)"
+        return _f64(p)
     p = _f64(p)
     assert p.ndim == 2 and p.shape[1] in (3, 4)
     if p.shape[1] == 3:
@@ -159,9 +177,9 @@ class Context:
         n = _f64(normals) if normals is not None else None
         c = _f64(covs) if covs is not None else None
         if n is not None:
-            assert n.shape == (p.shape[0], 4)
+            assert tuple(n.shape) == (p.shape[0], 4)
         if c is not None:
-            assert c.shape == (p.shape[0], 4, 4)
+            assert tuple(c.shape) == (p.shape[0], 4, 4)
         self._check(self._L.sgb_target_set_points(self._h, p.shape[0], _d(p), _d(n), _d(c)))
 
     def set_target_kdtree(self, nodes24, indices, root=0):
@@ -183,7 +201,7 @@ class Context:
         p = _points4(points)
         c = _f64(covs) if covs is not None else None
         if c is not None:
-            assert c.shape == (p.shape[0], 4, 4)
+            assert tuple(c.shape) == (p.shape[0], 4, 4)
         self._check(self._L.sgb_target_build_voxelmap(self._h, p.shape[0], _d(p), _d(c), float(leaf_size), int(search_offsets)))
 
     def target_batch_knn(self, queries, k=1):
@@ -203,7 +221,7 @@ class Context:
         p = _points4(points)
         c = _f64(covs) if covs is not None else None
         if c is not None:
-            assert c.shape == (p.shape[0], 4, 4)
+            assert tuple(c.shape) == (p.shape[0], 4, 4)
         self._check(self._L.sgb_source_set_points(self._h, p.shape[0], _d(p), _d(c)))
 
     @property
@@ -295,8 +313,14 @@ class Context:
     def estimate_features(self, points, num_neighbors=20, normals=True, covs=True):
         """estimate_normals_covariances (util/normal_estimation.hpp): returns (normals (N,4) | None, covs (N,4,4) | None)"""
         p = _points4(points)
-        n_out = np.empty((p.shape[0], 4)) if normals else None
-        c_out = np.empty((p.shape[0], 4, 4)) if covs else None
+        if _is_dev(p) and p.is_cuda:  # device in, device out
+            import torch
+
+            n_out = torch.empty((p.shape[0], 4), dtype=torch.float64, device=p.device) if normals else None
+            c_out = torch.empty((p.shape[0], 4, 4), dtype=torch.float64, device=p.device) if covs else None
+        else:
+            n_out = np.empty((p.shape[0], 4)) if normals else None
+            c_out = np.empty((p.shape[0], 4, 4)) if covs else None
         self._check(self._L.sgb_estimate_features(self._h, p.shape[0], _d(p), int(num_neighbors), _d(n_out), _d(c_out)))
         return n_out, c_out
 

@@ -395,6 +395,9 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   ctx->device = device_id;
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_entry, cudaEventDisableTiming);
+  for (int k = 0; k < sgb_ctx::kUploadChunks && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&ctx->ev_upload[k], cudaEventDisableTiming);
   // result slot in MAPPED page-locked host memory: the finishing CTA of a reduction writes H|b|e straight into it over PCIe, so the
   // host-returning calls (sgb_linearize / sgb_error) need no device-to-host copy behind the kernel, just the stream synchronisation
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_out), 64 * sizeof(double), cudaHostAllocMapped);
@@ -436,6 +439,13 @@ void sgb_destroy(sgb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   sgb_comm_disconnect(ctx);  // unmaps the peers' mailboxes
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  if (ctx->ev_entry) cudaEventDestroy(ctx->ev_entry);
+  for (int k = 0; k < sgb_ctx::kUploadChunks; k++)
+    if (ctx->ev_upload[k]) cudaEventDestroy(ctx->ev_upload[k]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;  // every DevBuf member frees its allocation (the context's device is current)
 }
@@ -607,15 +617,15 @@ int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   if (normals) {
     CU(ctx->stage_normals.reserve(n * 4 * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->stage_normals.p, normals, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stage_normals.p, normals, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CU(ctx->tgt_orig_normals.reserve(n * sizeof(float4)));
   }
   if (covs) {
     CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CU(ctx->tgt_orig_covA.reserve(n * sizeof(float4)));
     CU(ctx->tgt_orig_covB.reserve(n * sizeof(float4)));
   }
@@ -724,10 +734,10 @@ int sgb_target_set_voxelmap(sgb_ctx* ctx, double leaf_size, size_t n_voxels, con
   if (n_voxels == 0) return 0;
   const size_t n = n_voxels;
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, means, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, means, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   if (covs) {
     CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
     CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
   }
@@ -775,12 +785,8 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   CU(ctx->src_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (covs) {
     CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
-    CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
     CU(ctx->src_covA.reserve(n * sizeof(float4)));
     CU(ctx->src_covB.reserve(n * sizeof(float4)));
   }
@@ -800,34 +806,64 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
   CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
   CU(ctx->src_perm.reserve(n * sizeof(uint32_t)));
-  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->src_bounds.as<double>(), ctx->src_centre.as<double>(), ctx->sm_count, ctx->stream));
-  CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, covs ? ctx->stage_covs.as<double>() : nullptr, n, ctx->src_centre.as<double>(),
-                    ctx->tmp_pts.as<float4>(), nullptr, ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), ctx->keys_in.as<uint64_t>(),
-                    ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
-  // Morton order: consecutive lanes get spatially adjacent queries (coherent tree paths, coalesced gathers)
+  CU(ctx->src_rank.reserve(n * sizeof(uint32_t)));
   size_t temp_bytes = 0;
   CU(sort_pairs_u64_u32(nullptr, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
                         ctx->src_perm.as<uint32_t>(), n, ctx->stream));
   CU(ctx->sort_temp.reserve(temp_bytes));
+
+  // The upload is a two-stream pipeline.  The reference layout is 160 B / point, 128 of them the 4x4 double covariance: the points
+  // (32 B) go first on the context's stream and are centred, keyed, Hilbert-sorted and gathered WHILE the covariances travel in
+  // kUploadChunks pieces on the copy stream; each piece is packed (6 floats) and written straight to its place in the search order
+  // as soon as it has arrived, so that after the last byte only 1 / kUploadChunks of the conversion is left.  (Pageable host memory
+  // makes cudaMemcpyAsync stage synchronously: same result, no overlap.)  Device pointers are accepted too (cudaMemcpyDefault).
+  CU(cudaEventRecord(ctx->ev_entry, ctx->stream));           // everything queued so far (it may still read the staging buffers) ...
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_entry, 0));  // ... precedes the first chunk
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  const int n_chunks = covs ? static_cast<int>(std::min<size_t>(sgb_ctx::kUploadChunks, (n + 65535) / 65536)) : 0;
+  const size_t per_chunk = n_chunks ? (n + n_chunks - 1) / n_chunks : 0;
+  if (covs) {
+    // the chunks queue up behind the points on the same DMA engine: wait for the points' copy to have been ISSUED first
+    CU(cudaEventRecord(ctx->ev_entry, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_entry, 0));
+    for (int k = 0; k < n_chunks; k++) {
+      const size_t first = static_cast<size_t>(k) * per_chunk, cnt = std::min(per_chunk, n - first);
+      CU(cudaMemcpyAsync(ctx->stage_covs.as<double>() + first * 16, covs + first * 16, cnt * 16 * sizeof(double), cudaMemcpyDefault, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->ev_upload[k], ctx->copy_stream));
+    }
+  }
+  CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->src_bounds.as<double>(), ctx->src_centre.as<double>(), ctx->sm_count, ctx->stream));
+  CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, nullptr, n, ctx->src_centre.as<double>(), ctx->tmp_pts.as<float4>(), nullptr, nullptr, nullptr,
+                    ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+  // Hilbert order: consecutive lanes get spatially adjacent queries (coherent tree paths, coalesced gathers)
   CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
                         ctx->src_perm.as<uint32_t>(), n, ctx->stream));
-  // chunk-transposed Morton order: a lane walks K consecutive points of the curve, warp loads stay coalesced.
-  // K shrinks for small clouds so that there are still enough 32*K-point work units to fill the GPU.
   uint32_t K = 1;
 #ifdef SGB_PROFILING
-  if (const char* s = getenv("SGB_RUN")) K = static_cast<uint32_t>(atoi(s)) > 0 ? static_cast<uint32_t>(atoi(s)) : 1;  // chunk-transposed layout of the per-thread search (A/B)
-#endif
+  // chunk-transposed order of the per-thread search (A/B): a lane walks K consecutive points of the curve, warp loads stay coalesced
+  if (const char* s = getenv("SGB_RUN")) K = static_cast<uint32_t>(atoi(s)) > 0 ? static_cast<uint32_t>(atoi(s)) : 1;
   while (K > 1 && n / (32ull * K) < static_cast<size_t>(ctx->sm_count) * 16) K >>= 1;
-  ctx->src_run = K;
   if (K > 1) {
     CU(launch_chunk_transpose(ctx->src_perm.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), n, K, ctx->sm_count, ctx->stream));
     CU(cudaMemcpyAsync(ctx->src_perm.p, ctx->vals_in.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->launches += 1;
   }
-  CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_pts.as<float4>(), ctx->src_pts.as<float4>(), covs ? ctx->tmp_covA.as<float4>() : nullptr,
-                   ctx->src_covA.as<float4>(), covs ? ctx->tmp_covB.as<float4>() : nullptr, ctx->src_covB.as<float4>(), nullptr, nullptr, ctx->sm_count,
-                   ctx->stream));
+#endif
+  ctx->src_run = K;
+  CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_pts.as<float4>(), ctx->src_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                   ctx->sm_count, ctx->stream));
   ctx->launches += 5;
+  if (covs) {
+    CU(launch_inverse_perm(ctx->src_perm.as<uint32_t>(), n, ctx->src_rank.as<uint32_t>(), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    for (int k = 0; k < n_chunks; k++) {
+      const size_t first = static_cast<size_t>(k) * per_chunk, cnt = std::min(per_chunk, n - first);
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_upload[k], 0));
+      CU(launch_convert_cov_scatter(ctx->stage_covs.as<double>(), first, cnt, ctx->src_rank.as<uint32_t>(), ctx->src_covA.as<float4>(), ctx->src_covB.as<float4>(),
+                                    nullptr, nullptr, ctx->sm_count, ctx->stream));
+      ctx->launches += 1;
+    }
+  }
   return 0;
 }
 
@@ -880,7 +916,7 @@ int sgb_correspondences(sgb_ctx* ctx, uint64_t* target_index) {
   CU(launch_correspondences(ctx->corr.as<uint32_t>(), ctx->src_perm.as<uint32_t>(), ctx->n_src, ctx->tgt_pts.as<float4>(), ctx->tgt_is_voxel ? 1 : 0,
                             ctx->corr64.as<uint64_t>(), ctx->sm_count, ctx->stream));
   ctx->launches += 1;
-  CU(cudaMemcpyAsync(target_index, ctx->corr64.p, ctx->n_src * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(target_index, ctx->corr64.p, ctx->n_src * sizeof(uint64_t), cudaMemcpyDefault, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -155,7 +155,7 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
   if (n == 0 || (!out_normals && !out_covs)) return 0;
   CU(cudaSetDevice(ctx->device));
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   CU(ctx->pre_centre.reserve(4 * sizeof(double)));
   CU(ctx->pre_bounds.reserve(6 * sizeof(double)));
   CU(ctx->pre_pts.reserve(n * sizeof(float4)));
@@ -172,8 +172,8 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
                      nullptr, nullptr, nullptr, out_normals ? ctx->pre_out_normals.as<double>() : nullptr, out_covs ? ctx->pre_out_covs.as<double>() : nullptr,
                      depth, 0, ctx->stream));
   ctx->launches += 1;
-  if (out_normals) CU(cudaMemcpyAsync(out_normals, ctx->pre_out_normals.p, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_covs) CU(cudaMemcpyAsync(out_covs, ctx->pre_out_covs.p, n * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_normals) CU(cudaMemcpyAsync(out_normals, ctx->pre_out_normals.p, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  if (out_covs) CU(cudaMemcpyAsync(out_covs, ctx->pre_out_covs.p, n * 16 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -240,7 +240,7 @@ int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points, double 
   if (n == 0) return 0;
   CU(cudaSetDevice(ctx->device));
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
   CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
   CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));
@@ -267,7 +267,7 @@ int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points, double 
   CU(cudaMemcpyAsync(&count, ctx->pre_slots.as<uint32_t>() + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (count) {
-    CU(cudaMemcpyAsync(out_points, ctx->stage_covs.p, static_cast<size_t>(count) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_points, ctx->stage_covs.p, static_cast<size_t>(count) * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
   *n_out = count;
@@ -298,10 +298,10 @@ int sgb_target_build_voxelmap(sgb_ctx* ctx, size_t n, const double* points, cons
   CU(ctx->tgt_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, points, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   if (covs) {
     CU(ctx->stage_covs.reserve(n * 16 * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stage_covs.p, covs, n * 16 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   }
   CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
   CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
@@ -368,14 +368,14 @@ int sgb_target_batch_knn(sgb_ctx* ctx, size_t n_queries, const double* queries, 
     return 0;
   }
   CU(ctx->stage_pts.reserve(n * 4 * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->stage_pts.p, queries, n * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->stage_pts.p, queries, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   CU(ctx->pre_out_covs.reserve(nk * sizeof(double)));
   CU(ctx->corr64.reserve(nk * sizeof(uint64_t)));
   CU(launch_batch_knn(ctx->tgt_pnodes.as<float4>(), ctx->tgt_pts.as<float4>(), ctx->stage_pts.as<double>(), static_cast<uint32_t>(n), k, ctx->tgt_centre.as<double>(),
                       ctx->corr64.as<unsigned long long>(), ctx->pre_out_covs.as<double>(), ctx->tree_depth, ctx->stream));
   ctx->launches += 1;
-  CU(cudaMemcpyAsync(out_indices, ctx->corr64.p, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(out_sq_dists, ctx->pre_out_covs.p, nk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_indices, ctx->corr64.p, nk * sizeof(uint64_t), cudaMemcpyDefault, ctx->stream));
+  CU(cudaMemcpyAsync(out_sq_dists, ctx->pre_out_covs.p, nk * sizeof(double), cudaMemcpyDefault, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -45,6 +45,12 @@ struct sgb_ctx {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  // second stream + events of the pipelined source upload (sgb_source_set_points): the covariance chunks travel on it while the
+  // context's stream converts / orders the points and the chunks that have already arrived
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int kUploadChunks = 8;
+  cudaEvent_t ev_upload[kUploadChunks] = {};
+  cudaEvent_t ev_entry = nullptr;
   std::string err;
   uint64_t launches = 0;
   // The product library has ONE search path (grid front end + packet / pending search, then the factor kernel).  The fields below that
@@ -87,7 +93,7 @@ struct sgb_ctx {
   // ---- source ----
   size_t n_src = 0;
   bool src_has_covs = false;
-  sgb::DevBuf src_pts, src_covA, src_covB, src_perm, src_centre, src_bounds;
+  sgb::DevBuf src_pts, src_covA, src_covB, src_perm, src_rank, src_centre, src_bounds;
   uint32_t src_run = 1;  // K of the chunk-transposed source layout (DevSource::run)
 
   // ---- scratch ----

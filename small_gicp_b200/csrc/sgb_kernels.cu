@@ -435,6 +435,28 @@ __global__ void convert_kernel(const double4* __restrict__ pts, const double4* _
   }
 }
 
+// rank[perm[j]] = j: where the point with original index i ends up in the search order
+__global__ void inverse_perm_kernel(const uint32_t* __restrict__ perm, size_t n, uint32_t* rank) {
+  for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < n; j += static_cast<size_t>(gridDim.x) * blockDim.x) rank[perm[j]] = static_cast<uint32_t>(j);
+}
+
+// one CHUNK of raw 4x4 double covariances (original indices first .. first + n) -> packed floats written straight to their place in
+// the search order (and, optionally, to the original-order copy): the chunk is converted while the next one is still on the PCIe bus
+__global__ void convert_cov_scatter_kernel(const double* __restrict__ covs, size_t first, size_t n, const uint32_t* __restrict__ rank, float4* outA,
+                                           float4* outB, float4* origA, float4* origB) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double* c = covs + (first + i) * 16;
+    const float4 a = pack_covA(c), b = pack_covB(c);
+    const uint32_t r = rank[first + i];
+    outA[r] = a;
+    outB[r] = b;
+    if (origA) {
+      origA[first + i] = a;
+      origB[first + i] = b;
+    }
+  }
+}
+
 // curve keys of points that are already on the device in centred FP32 form (target: device-side tree construction)
 __global__ void curve_keys_kernel(const float4* __restrict__ pts, size_t n, const double* __restrict__ centre, uint64_t* keys, uint32_t* vals) {
   const double inv_ext = 2097151.0 / centre[3], h = 0.5 * centre[3];
@@ -677,6 +699,19 @@ cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const
   if (!n) return cudaSuccess;
   convert_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(reinterpret_cast<const double4*>(d_pts4), reinterpret_cast<const double4*>(d_normals4), d_covs16,
                                                                  n, d_centre4, out_pts, out_normals, out_covA, out_covB, keys, vals);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inverse_perm(const uint32_t* perm, size_t n, uint32_t* rank, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  inverse_perm_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(perm, n, rank);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_cov_scatter(const double* d_covs16, size_t first, size_t n, const uint32_t* rank, float4* outA, float4* outB, float4* origA,
+                                       float4* origB, int sm_count, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  convert_cov_scatter_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(d_covs16, first, n, rank, outA, outB, origA, origB);
   return cudaGetLastError();
 }
 
