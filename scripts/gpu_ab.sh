@@ -1,28 +1,24 @@
 #!/bin/bash
-# A/B visit: parity tests (default switches, then under the first non-default spec), then bench.py once per spec.
-#   bash scripts/gpu_ab.sh TAG SPEC [SPEC ...]     SPEC = "-" (defaults) or "VAR=val,VAR2=val2"
+# A/B of profiling-library switches on the bench line (no extras, no CPU leg).  Usage: bash scripts/gpu_ab2.sh <tag> "name:ENV=v,ENV=v" ...
+# Each variant runs in its own process with SGB_LIBRARY=prof (libsgicp_b200_prof.so reads the SGB_* switches); "product" = the shipped library.
 TAG=$1; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-T0=$(date +%s)
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py tests/test_gpu_fused_allreduce.py tests/test_host_mirror.py -q -m gpu -x > $OUT/pytest.log 2>&1; echo "rc=$?" >> $OUT/pytest.log
-tail -3 $OUT/pytest.log; echo "t=$(( $(date +%s) - T0 ))s"
-LAST="${@: -1}"
-if [ "$LAST" != "-" ]; then
-  env $(echo $LAST | tr ',' ' ') timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "structures or far_and or synthetic_200k or golden or degenerate" > $OUT/pytest_variant.log 2>&1; echo "rc=$?" >> $OUT/pytest_variant.log
-  echo "variant [$LAST]:"; tail -3 $OUT/pytest_variant.log; echo "t=$(( $(date +%s) - T0 ))s"
-fi
-i=0
 for spec in "$@"; do
-  i=$((i+1))
-  envs=""; [ "$spec" != "-" ] && envs=$(echo $spec | tr ',' ' ')
-  env $envs timeout 200 python bench.py --steps 40 --warmup 3 --no-cpu-baseline > $OUT/bench_$i.json 2> $OUT/bench_$i.err; echo "rc=$?" >> $OUT/bench_$i.err
+  name=${spec%%:*}; envs=${spec#*:}
+  [ "$envs" = "$spec" ] && envs=""
+  (
+    if [ "$name" != "product" ]; then export SGB_LIBRARY=prof; fi
+    IFS=',' read -ra kv <<< "$envs"
+    for e in "${kv[@]}"; do [ -n "$e" ] && export "$e"; done
+    timeout 300 python bench.py --steps 40 --warmup 5 --no-extras --no-cpu-baseline > $OUT/$name.json 2> $OUT/$name.err
+  )
   python - <<PY
 import json
 try:
-    d=json.load(open("$OUT/bench_$i.json")); print("[$spec] value", round(d["value"],1), "ms", round(d["ms_per_step"],4), "warm", round(d["value_l2_warm"],1), "per_pose", [round(x,4) for x in d["per_pose_ms"]], "clocks", d["clocks"]["sm_mhz"])
+    d=json.loads(open("$OUT/$name.json").read().strip().splitlines()[-1])
+    print("%-28s ms/step %.4f  per pose %s  e2e %.3f  err %.4f" % ("$name", d["ms_per_step"], " ".join("%.4f"%x for x in d["per_pose_ms"]), d["e2e"]["ms_per_step"], d["error_ms"]["value"]))
 except Exception as e:
-    print("[$spec] fail", e); print(open("$OUT/bench_$i.err").read()[-1500:])
+    print("$name", "FAILED", e); print(open("$OUT/$name.err").read()[-1500:])
 PY
 done
-echo "t=$(( $(date +%s) - T0 ))s"

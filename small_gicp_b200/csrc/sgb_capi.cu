@@ -197,6 +197,7 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
       if (sgrid > scap) sgrid = scap;
       const uint8_t* settled = nullptr;
       const uint32_t* pending_count = nullptr;
+      ChunkClasses cc = {};
       // more pending queries than this: packet search over the chunk-ordered queries, else a warp per pending query
       const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / static_cast<size_t>(ctx->pending_div));
       if (ctx->grid_ready) {
@@ -216,8 +217,27 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
         uint32_t* pbase = ctx->grid_pending.as<uint32_t>();
         uint32_t* pc = pbase + ctx->pending_parity;
         uint32_t* plist = pbase + 2;
+        if (ctx->grid_blocks && ctx->use_chunk_classes) {
+          // work lists of the packet search by cost class; counters alternate like the pending counters (sized in sgb_source_set_points)
+          const uint32_t nck = static_cast<uint32_t>((ctx->n_src + 31) / 32);
+          const void* cb = ctx->chunk_lists.p;
+          CU(ctx->chunk_lists.reserve((8 + static_cast<size_t>(kChunkClasses) * nck) * sizeof(uint32_t)));
+          if (ctx->chunk_lists.p != cb || !ctx->chunk_lists_clean) {
+            CU(cudaMemsetAsync(ctx->chunk_lists.p, 0, 8 * sizeof(uint32_t), ctx->stream));
+            ctx->chunk_lists_clean = true;
+          }
+          uint32_t* cbase = ctx->chunk_lists.as<uint32_t>();
+          cc.count = cbase + 4 * ctx->pending_parity;
+          cc.count_next = cbase + 4 * (ctx->pending_parity ^ 1);
+          cc.lists = cbase + 8;
+          cc.n_chunks = nck;
+          const float cell = ctx->grid_cell;
+          cc.wide_r2 = ctx->class_wide_cells * ctx->class_wide_cells * cell * cell;  // search balls wider than two cells / one cell
+          cc.mid_r2 = cell * cell;
+          cc.fallback_pct = ctx->class_fallback_pct;
+        }
         CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->probe_batch_tail, ctx->grid_state.as<uint8_t>(), pc,
-                             plist, pbase + (ctx->pending_parity ^ 1), ctx->stream));
+                             plist, pbase + (ctx->pending_parity ^ 1), cc, ctx->stream));
         ctx->pending_parity ^= 1;
         CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, plist, pending_split, ctx->grid_pts.as<float4>(),
                                  (ctx->grid_blocks && ctx->use_ring) ? ctx->grid_table.as<GridSlot>() : nullptr, ctx->grid_capacity, g, ctx->sm_count * 8,
@@ -236,7 +256,7 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
         queue_next = ctx->packet_queue.as<uint32_t>() + (ctx->packet_parity ^ 1);
         ctx->packet_parity ^= 1;
       }
-      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, ctx->stream));
+      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, cc, ctx->tma_leaf, ctx->stream));
 #ifdef SGB_PROFILING
       if (ctx->debug_pending && pending_count) {  // profiling aid: synchronises
         uint32_t h = 0;
@@ -422,6 +442,10 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   }
   if (const char* s = getenv("SGB_PROBE_TAIL")) ctx->probe_batch_tail = (s[0] == '1');        // 1 = probe scans its list in clamped batches of eight (A/B, sgb_grid.cu)
   if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
+  if (const char* s = getenv("SGB_CHUNK_CLASSES")) ctx->use_chunk_classes = !(s[0] == '0');  // 0 = no work lists by cost class: chunks in curve order
+  if (const char* s = getenv("SGB_TMA_LEAF")) ctx->tma_leaf = (s[0] == '1');  // 1 = dense leaf scans read a cp.async.bulk (TMA) staged copy of the leaf
+  if (const char* s = getenv("SGB_CLASS_FALLBACK_PCT")) ctx->class_fallback_pct = static_cast<uint32_t>(std::max(0, atoi(s)));
+  if (const char* s = getenv("SGB_CLASS_WIDE")) ctx->class_wide_cells = static_cast<float>(atof(s));
   ctx->debug_pending = getenv("SGB_DEBUG_PENDING") != nullptr;
   if (const char* s = getenv("SGB_TREE")) {  // profiling switch: "host" = kd-tree built on the host, "lbvh" = Hilbert-order linear BVH without refinement
     ctx->host_tree = (s[0] == 'h');
@@ -802,6 +826,11 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
     if (ctx->grid_pending.p != before) ctx->pending_clean = false;
   }
   if (int rc = ensure_reduction_buffers(ctx, ctx->sm_count * 8)) return rc;
+  {
+    const void* before = ctx->chunk_lists.p;
+    CU(ctx->chunk_lists.reserve((8 + static_cast<size_t>(kChunkClasses) * ((n + 31) / 32)) * sizeof(uint32_t)));
+    if (ctx->chunk_lists.p != before) ctx->chunk_lists_clean = false;
+  }
   CU(ctx->keys_in.reserve(n * sizeof(uint64_t)));
   CU(ctx->keys_out.reserve(n * sizeof(uint64_t)));
   CU(ctx->vals_in.reserve(n * sizeof(uint32_t)));

@@ -80,6 +80,12 @@ struct sgb_ctx {
   bool pending_clean = false;  // both pending counters are zero / maintained by the probe kernels
   int pending_parity = 0;
   sgb::DevBuf packet_queue;      // two alternating chunk-queue counters of the packet search (each launch clears the other)
+  sgb::DevBuf chunk_lists;       // [2 parities][3] class counters, then [3][n_chunks] chunk ids: the packet search's work lists, filled by the probe
+  bool chunk_lists_clean = false;
+  uint32_t class_fallback_pct = 85;  // more than this share of the chunks listed (pending lanes almost everywhere): curve order instead of the lists
+  float class_wide_cells = 2.0f;     // search radius (in cells) from which a chunk counts as wide
+  bool tma_leaf = false;         // profiling switch SGB_TMA_LEAF=1 (A/B of the north-star's TMA leaf staging)
+  bool use_chunk_classes = true; // profiling switch SGB_CHUNK_CLASSES=0: the packet search scans all chunks in curve order
   int packet_parity = 0;
   bool use_packet_queue = true;  // profiling switch SGB_PACKET_QUEUE=0: static stride
   bool probe_batch_tail = false; // A/B switch SGB_PROBE_TAIL=1: block-list scan in clamped batches of eight (measured: no gain)

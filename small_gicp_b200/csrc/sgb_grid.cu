@@ -227,10 +227,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 template <int MIN_CTAS, bool BATCH_TAIL>
 __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
-                                                               uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
+                                                               uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, ChunkClasses cc) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = gi < P.src.n;
   if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
+  if (gi < kChunkClasses && cc.count_next) cc.count_next[gi] = 0u;
   const uint32_t i = in_range ? gi : P.src.n - 1u;
   const double* R = P.T;
   const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
@@ -290,26 +291,67 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
   const bool settled = best != kNone && best_d <= g.settle_d2;
   if (!settled && P.use_prev) {  // keep the better of (grid candidate, previous correspondence) as the tree search's seed
     const uint32_t prev = P.corr[i];
-    if (prev != kNone && best == kNone) best = prev;
-    else if (prev != kNone) {
+    if (prev != kNone) {
       const float4 t = __ldg(&P.tgt.pts[prev]);
       const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-      if (dx * dx + dy * dy + dz * dz < best_d) best = prev;
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < best_d) {  // (a seed beyond the rejector's bound is no use: best_d starts there)
+        best = prev;
+        best_d = d;
+      }
     }
   }
   if (in_range) {
     P.corr[i] = best;
     state[i] = settled ? 1 : 0;
   }
+  // Pending queries go to a compact list, and -- for the packet search -- the CHUNK (one warp here = one 32-query chunk there) goes into
+  // the work list of its cost class = how far its widest search ball reaches (best_d is the squared radius a pending lane starts its
+  // walk with).  The packet search takes the wide classes first, so that what is left when the GPU drains are the cheap walks
+  // (profiles/r01/ai: a third of that kernel was a tail of late-starting heavy chunks); chunks without a pending lane are in no list.
+  // Both appends are aggregated over the CTA's eight warps: at most four atomics per CTA -- one per warp and list made the hot
+  // counters the probe's own tail (r02d: +9 us at the identity pose).
   const bool pend = in_range && !settled;
   const unsigned m = __ballot_sync(0xffffffffu, pend);
-  if (m) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == static_cast<uint32_t>(__ffs(m) - 1)) base = atomicAdd(pending_count, static_cast<uint32_t>(__popc(m)));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (pend) pending_list[base + __popc(m & ((1u << lane) - 1u))] = i;
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  __shared__ uint32_t s_cnt[8], s_cls[8], s_base[8];
+  {
+    const uint32_t r2 = __reduce_max_sync(0xffffffffu, pend ? __float_as_uint(best_d) : 0u);  // non-negative floats order like their bits
+    if (lane == 0) {
+      const float r = __uint_as_float(r2);
+      s_cnt[wib] = static_cast<uint32_t>(__popc(m));
+      s_cls[wib] = !m ? kChunkClasses : (r >= cc.wide_r2 ? 0u : (r >= cc.mid_r2 ? 1u : 2u));
+    }
   }
+  __syncthreads();
+  if (wib == 0) {
+    const uint32_t nw = blockDim.x >> 5;
+    const uint32_t cnt = lane < nw ? s_cnt[lane] : 0u, cls = lane < nw ? s_cls[lane] : kChunkClasses;
+    uint32_t incl = cnt;  // inclusive prefix over the warps
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= static_cast<uint32_t>(o)) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+    uint32_t pbase = 0;
+    if (lane == 0 && total) pbase = atomicAdd(pending_count, total);
+    pbase = __shfl_sync(0xffffffffu, pbase, 0);
+    if (lane < nw) s_base[lane] = pbase + incl - cnt;
+    if (cc.lists) {
+#pragma unroll
+      for (uint32_t c = 0; c < kChunkClasses; c++) {
+        const unsigned mc = __ballot_sync(0xffffffffu, cls == c);
+        if (!mc) continue;
+        uint32_t cb = 0;
+        if (lane == static_cast<uint32_t>(__ffs(mc) - 1)) cb = atomicAdd(&cc.count[c], static_cast<uint32_t>(__popc(mc)));
+        cb = __shfl_sync(0xffffffffu, cb, __ffs(mc) - 1);
+        if (cls == c) cc.lists[static_cast<size_t>(c) * cc.n_chunks + cb + __popc(mc & ((1u << lane) - 1u))] = (blockIdx.x * blockDim.x >> 5) + lane;
+      }
+    }
+  }
+  __syncthreads();
+  if (pend) pending_list[s_base[wib] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -551,7 +593,8 @@ cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_s
 }
 
 cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st) {
+                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, const ChunkClasses& cc,
+                              cudaStream_t st) {
   // *pending_count must be zero on entry: the previous probe (or the context) cleared it
   const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
@@ -562,15 +605,15 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
   }
   static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;
   if (batch_tail) {
-    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
     return cudaGetLastError();
   }
   if (ctas == 6) {
-    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
     return cudaGetLastError();
   }
   if (ctas == 8) {
-    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
     return cudaGetLastError();
   }
 #else
@@ -578,7 +621,7 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
   (void)batch_tail;
   (void)cell;
 #endif
-  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count);
+  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
   return cudaGetLastError();
 }
 

@@ -62,11 +62,22 @@ cudaError_t launch_chunk_transpose(const uint32_t* in, uint32_t* out, size_t n, 
 cudaError_t sort_pairs_u64_u32(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                                size_t n, cudaStream_t st);
 
+/// Work lists of the packet search, filled by the probe (one warp of the probe = one 32-query chunk): chunk ids by cost class
+/// (0 = widest search ball ... kChunkClasses - 1 = narrowest), so that the packet search can take the expensive walks first.
+constexpr uint32_t kChunkClasses = 3;
+struct ChunkClasses {
+  uint32_t* count;       // [kChunkClasses] entries of each list (zero on entry: the previous probe cleared them)
+  uint32_t* count_next;  // [kChunkClasses] the counters of the NEXT linearize (this probe clears them)
+  uint32_t* lists;       // [kChunkClasses][n_chunks] chunk ids, or null: no lists (the packet search scans the settled flags itself)
+  uint32_t n_chunks;
+  float wide_r2, mid_r2;  // class boundaries on the squared search radius
+  uint32_t fallback_pct;  // more than this share of all chunks listed (i.e. with pending lanes): the packet search ignores the lists (curve order)
+};
 // sgb_kernels_packet.cu
 int packet_occupancy(int max_depth);
 /// queue / queue_next: two alternating zero-initialised counters of the dynamic chunk queue (this launch clears queue_next), or null = static stride
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
-                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, cudaStream_t st);
+                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, const ChunkClasses& cc, bool tma_leaf, cudaStream_t st);
 // sgb_grid.cu: uniform-grid front end of the search
 struct GridParams {
   float origin[3];  // minimum corner of the target's box (centred frame)
@@ -86,7 +97,8 @@ cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_s
 /// points, or a few far outliers stretching the box so that the cell-count bound inflates the cell) and the exact tree search alone is used
 constexpr uint32_t kGridMaxList = 2048;
 cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, cudaStream_t st);
+                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, const ChunkClasses& cc,
+                              cudaStream_t st);
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
                                   uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
                                   cudaStream_t st);

@@ -13,6 +13,7 @@
 // children (64 B, "BVH2" layout):  float4[4] = {L.lo|L.a, L.hi|L.b, R.lo|R.a, R.hi|R.b} where a child is a leaf
 // (a = first point, b = count > 0) or an inner node (a = node index, b = 0).
 #include <cfloat>
+#include <cstdlib>
 
 #include "sgb_device.cuh"
 #include "sgb_kernels.h"
@@ -31,9 +32,39 @@ __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const f
   return dx * dx + dy * dy + dz * dz;
 }
 
+// ---- TMA staging of a leaf's point block (BASELINE north_star: "TMA bulk loads for the leaf point blocks") ----------------------
+// One elected lane arms the warp's mbarrier with the byte count and issues ONE cp.async.bulk (SASS UBLKCP) for the leaf's contiguous
+// <= 32 x 16 B; the warp waits on the barrier's phase and then reads the points from shared memory.  TMA_LEAF is a compile-time A/B:
+// measured in profiles/r02 (the broadcast __ldg path below serves an L1-resident leaf in ~32 cycles per load, pipelined; the bulk copy
+// always makes the round trip through L2) -- see DESIGN.md §4 for the numbers and which variant ships.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void bulk_load_leaf(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar)), d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(b), "r"(phase)
+      : "memory");
+  }
+}
+
+template <bool TMA_LEAF>
 __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
                                                                   const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
-                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next) {
+                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, ChunkClasses cc) {
   // Work distribution: chunks (32 consecutive queries) differ wildly in cost -- all lanes settled by the grid probe, or 32
   // tree walks through a misaligned wall -- and a static stride left a third of the warps idle for the second half of the
   // kernel (profiles/r01/ai: 39-52 % achieved occupancy of 75 %).  With `queue` the warps take their first chunk by rank and
@@ -46,6 +77,14 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
   if (pending_count && *pending_count <= min_pending) return;
   extern __shared__ float s_dist[];  // [max_depth][kLinBlock] per-lane box distance of each pending subtree
   __shared__ uint2 s_child[kPktWarps][40];  // per-warp: the pending subtrees themselves (warp-uniform)
+  __shared__ __align__(128) float4 s_leaf[TMA_LEAF ? kPktWarps : 1][32];  // TMA landing zone of the warp's current leaf
+  __shared__ __align__(8) uint64_t s_bar[TMA_LEAF ? kPktWarps : 1];
+  uint32_t tma_phase = 0;
+  if (TMA_LEAF) {
+    if ((threadIdx.x & 31u) == 0) mbar_init(&s_bar[threadIdx.x >> 5], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
   const double* R = P.T;
   const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
   const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
@@ -54,23 +93,38 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
   const float4* __restrict__ pts = P.tgt.pts;
   const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_chunks = (P.src.n + 31u) >> 5;
   float* my_dist = s_dist + threadIdx.x;
   uint2* my_child = s_child[wib];
+  // What there is to do: with the probe's class lists (cc.lists) the work items are the chunks that have a pending lane, the widest
+  // search balls first -- positions [0, n0) of the virtual sequence are class 0, [n0, n0 + n1) class 1, ... -- so that the GPU drains
+  // on cheap walks; without lists every chunk of the source is an item and the settled flags are consulted here.
+  uint32_t c0 = 0, c1 = 0, n_items = (P.src.n + 31u) >> 5;
+  if (cc.lists) {
+    c0 = cc.count[0];
+    c1 = c0 + cc.count[1];
+    // The lists are in the order the probe's warps happened to finish: neighbouring items are NOT neighbouring chunks, so the warps of
+    // an SM no longer share tree nodes through L1.  When nearly every chunk has pending lanes anyway (a grossly misaligned first
+    // iteration: nothing to skip, no cheap tail to save for the end) the curve order wins (r02d: 0.2335 vs 0.2441 ms at T0, 0.1936 vs 0.1795 ms at T1).
+    const uint32_t listed = c1 + cc.count[2];
+    if (listed * 100u > n_items * cc.fallback_pct) cc.lists = nullptr;
+    else n_items = listed;
+  }
 
-  for (uint32_t chunk = warp; chunk < n_chunks;) {
+  for (uint32_t item = warp; item < n_items;) {
+    uint32_t chunk = item;
+    if (cc.lists) chunk = item < c0 ? cc.lists[item] : (item < c1 ? cc.lists[cc.n_chunks + (item - c0)] : cc.lists[2u * cc.n_chunks + (item - c1)]);
     const uint32_t i = chunk * 32u + lane;
-    // the chunk after this one: from the queue (dynamic) or by stride (static)
-    uint32_t next_chunk = chunk + n_warps;
+    // the item after this one: from the queue (dynamic) or by stride (static)
+    uint32_t next_item = item + n_warps;
     if (queue) {
-      if (lane == 0) next_chunk = n_warps + atomicAdd(queue, 1u);
-      next_chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+      if (lane == 0) next_item = n_warps + atomicAdd(queue, 1u);
+      next_item = __shfl_sync(0xffffffffu, next_item, 0);
     }
     // with the grid front end (sgb_grid.cu) most queries are already settled; only the pending ones walk the tree,
     // seeded with the candidate the grid probe left in corr[]
     const bool valid = i < P.src.n && !(settled && settled[i]);
     if (!__any_sync(0xffffffffu, valid)) {
-      chunk = next_chunk;
+      item = next_item;
       continue;
     }
     float fx = 0.f, fy = 0.f, fz = 0.f;
@@ -166,9 +220,16 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
       if (__popc(want) > kPacketDenseLanes) {
         // many interested lanes: every lane tests every point (uniform addresses -> one broadcast load per point)
         const float4* lp = pts + leaf_first;
+        if (TMA_LEAF && leaf_cnt <= 32u) {
+          __syncwarp();  // everybody is done with the previous leaf in the landing zone
+          if (lane == 0) bulk_load_leaf(s_leaf[wib], lp, leaf_cnt * 16u, &s_bar[wib]);
+          mbar_wait(&s_bar[wib], tma_phase);
+          tma_phase ^= 1u;
+          lp = s_leaf[wib];
+        }
 #pragma unroll 4
         for (uint32_t j = 0; j < leaf_cnt; j++) {
-          const float4 t = __ldg(&lp[j]);
+          const float4 t = (TMA_LEAF && leaf_cnt <= 32u) ? lp[j] : __ldg(&lp[j]);
           const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
           const float d = dx * dx + dy * dy + dz * dz;
           if (d < best_d) {
@@ -207,26 +268,36 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
     }
     __syncwarp();
     if (valid) P.corr[i] = best;
-    chunk = next_chunk;
+    item = next_item;
   }
 }
 
 int packet_occupancy(int max_depth) {
   int nb = 0;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel, kLinBlock, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel<false>, kLinBlock, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
-                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, cudaStream_t st) {
+                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, const ChunkClasses& cc, bool tma_leaf, cudaStream_t st) {
   if (max_depth > 40) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
+#ifdef SGB_PROFILING
+  if (tma_leaf) {  // A/B (SGB_TMA_LEAF=1): leaf blocks staged by cp.async.bulk + mbarrier
+    if (!settled) {
+      packet_search_kernel<true><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+      return cudaGetLastError();
+    }
+    return launch_dependent(packet_search_kernel<true>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+  }
+#endif
   if (!settled) {  // no grid front end: nothing on the stream this launch could overlap with
-    packet_search_kernel<<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next);
+    packet_search_kernel<false><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
     return cudaGetLastError();
   }
-  return launch_dependent(packet_search_kernel, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next);
+  (void)tma_leaf;
+  return launch_dependent(packet_search_kernel<false>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
 }
 
 }  // namespace sgb

@@ -345,7 +345,8 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     tc, tt, sc, Tgt, nt = synthetic_pair
     sg = _sg()
     results = {}
-    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_PROBE_TAIL")
+    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_PROBE_TAIL", "SGB_TMA_LEAF",
+                "SGB_CHUNK_CLASSES", "SGB_CLASS_FALLBACK_PCT")
     for name, env, own in (
         ("device-kd/grid", {}, True),
         ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
@@ -359,6 +360,11 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
         ("device-kd/grid-small-cells-warp", {"SGB_GRID_CELL": "0.7", "SGB_PENDING_DIV": "1"}, True),
         ("device-kd/grid-large-cells", {"SGB_GRID_CELL": "6"}, True),
         ("device-kd/grid-batched-tail", {"SGB_PROBE_TAIL": "1"}, True),
+        ("device-kd/packet-tma-leaf", {"SGB_PENDING_DIV": "1000000", "SGB_TMA_LEAF": "1"}, True),
+        ("device-kd/no-grid-tma-leaf", {"SGB_GRID": "0", "SGB_TMA_LEAF": "1"}, True),
+        ("device-kd/packet-no-class-lists", {"SGB_PENDING_DIV": "1000000", "SGB_CHUNK_CLASSES": "0"}, True),
+        ("device-kd/packet-class-lists-always", {"SGB_PENDING_DIV": "1000000", "SGB_CLASS_FALLBACK_PCT": "100"}, True),
+        ("device-kd/packet-class-lists-never", {"SGB_PENDING_DIV": "1000000", "SGB_CLASS_FALLBACK_PCT": "0"}, True),
         ("device-lbvh/grid", {"SGB_TREE": "lbvh"}, True),
         ("host-kd/packet", {"SGB_TREE": "host"}, True),
         ("reference-kd/packet", {}, False),
