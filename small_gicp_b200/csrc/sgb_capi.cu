@@ -654,10 +654,16 @@ int sgb_target_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
     CU(ctx->tgt_orig_covB.reserve(n * sizeof(float4)));
   }
   CU(ctx->tgt_orig_pts.reserve(n * sizeof(float4)));
+  float4* lo = nullptr;
+  if (!normals || !covs) {  // features may still be estimated on the device (sgb_target_estimate_features): keep the rounding residuals
+    CU(ctx->tgt_orig_lo.reserve(n * sizeof(float4)));
+    lo = ctx->tgt_orig_lo.as<float4>();
+  }
+  ctx->tgt_has_lo = lo != nullptr;
   CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->tgt_bounds.as<double>(), ctx->tgt_centre.as<double>(), ctx->sm_count, ctx->stream));
   CU(launch_convert(ctx->stage_pts.as<double>(), normals ? ctx->stage_normals.as<double>() : nullptr, covs ? ctx->stage_covs.as<double>() : nullptr, n,
                     ctx->tgt_centre.as<double>(), ctx->tgt_orig_pts.as<float4>(), ctx->tgt_orig_normals.as<float4>(), ctx->tgt_orig_covA.as<float4>(),
-                    ctx->tgt_orig_covB.as<float4>(), nullptr, nullptr, ctx->sm_count, ctx->stream));
+                    ctx->tgt_orig_covB.as<float4>(), nullptr, nullptr, ctx->sm_count, ctx->stream, lo));
   ctx->launches += 4;
   // pageable host memory: the async copies above are staged synchronously, nothing else borrows the inputs
   return 0;
@@ -862,8 +868,14 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
     }
   }
   CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->src_bounds.as<double>(), ctx->src_centre.as<double>(), ctx->sm_count, ctx->stream));
+  float4* lo = nullptr;
+  if (!covs) {  // covariances may still be estimated on the device (sgb_source_estimate_features): keep the rounding residuals
+    CU(ctx->tmp_lo.reserve(n * sizeof(float4)));
+    lo = ctx->tmp_lo.as<float4>();
+  }
+  ctx->src_has_lo = lo != nullptr;
   CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, nullptr, n, ctx->src_centre.as<double>(), ctx->tmp_pts.as<float4>(), nullptr, nullptr, nullptr,
-                    ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream));
+                    ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->sm_count, ctx->stream, lo));
   // Hilbert order: consecutive lanes get spatially adjacent queries (coherent tree paths, coalesced gathers)
   CU(sort_pairs_u64_u32(ctx->sort_temp.p, temp_bytes, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(),
                         ctx->src_perm.as<uint32_t>(), n, ctx->stream));

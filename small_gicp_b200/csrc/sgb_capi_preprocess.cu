@@ -159,9 +159,10 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
   CU(ctx->pre_centre.reserve(4 * sizeof(double)));
   CU(ctx->pre_bounds.reserve(6 * sizeof(double)));
   CU(ctx->pre_pts.reserve(n * sizeof(float4)));
+  CU(ctx->pre_lo.reserve(n * sizeof(float4)));
   CU(launch_bounds_centre(ctx->stage_pts.as<double>(), n, ctx->pre_bounds.as<double>(), ctx->pre_centre.as<double>(), ctx->sm_count, ctx->stream));
   CU(launch_convert(ctx->stage_pts.as<double>(), nullptr, nullptr, n, ctx->pre_centre.as<double>(), ctx->pre_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr,
-                    nullptr, ctx->sm_count, ctx->stream));
+                    nullptr, ctx->sm_count, ctx->stream, ctx->pre_lo.as<float4>()));
   ctx->launches += 4;
   int depth = 0;
   if (int rc = build_lbvh(ctx, ctx->pre_pts.as<float4>(), n, ctx->pre_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
@@ -170,7 +171,7 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
   const int mode = (out_normals ? 1 : 0) | (out_covs ? 2 : 0);
   CU(launch_features(ctx->pre_nodes.as<float4>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->pre_centre.as<double>(), mode,
                      nullptr, nullptr, nullptr, out_normals ? ctx->pre_out_normals.as<double>() : nullptr, out_covs ? ctx->pre_out_covs.as<double>() : nullptr,
-                     depth, 0, ctx->stream));
+                     depth, 0, ctx->stream, ctx->pre_lo.as<float4>()));
   ctx->launches += 1;
   if (out_normals) CU(cudaMemcpyAsync(out_normals, ctx->pre_out_normals.p, n * 4 * sizeof(double), cudaMemcpyDefault, ctx->stream));
   if (out_covs) CU(cudaMemcpyAsync(out_covs, ctx->pre_out_covs.p, n * 16 * sizeof(double), cudaMemcpyDefault, ctx->stream));
@@ -193,7 +194,8 @@ int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
   // the target's own tree and leaf-ordered points are already resident: write the features straight into the leaf-ordered streams
   CU(launch_features(ctx->tgt_pnodes.as<float4>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->tgt_centre.as<double>(), 3,
-                     ctx->tgt_normals.as<float4>(), ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->tree_depth, 1, ctx->stream));
+                     ctx->tgt_normals.as<float4>(), ctx->tgt_covA.as<float4>(), ctx->tgt_covB.as<float4>(), nullptr, nullptr, ctx->tree_depth, 1, ctx->stream,
+                     ctx->tgt_has_lo ? ctx->tgt_orig_lo.as<float4>() : nullptr));
   ctx->launches += 1;
   // keep the ORIGINAL-order copies in step (a later sgb_target_build_kdtree / _set_kdtree re-gathers the leaf-ordered streams from them)
   CU(ctx->tgt_orig_normals.reserve(n * sizeof(float4)));
@@ -223,7 +225,7 @@ int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   CU(ctx->src_covA.reserve(n * sizeof(float4)));
   CU(ctx->src_covB.reserve(n * sizeof(float4)));
   CU(launch_features(ctx->pre_nodes.as<float4>(), ctx->pre_leaf_pts.as<float4>(), static_cast<uint32_t>(n), num_neighbors, ctx->src_centre.as<double>(), 2, nullptr,
-                     ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), nullptr, nullptr, depth, 0, ctx->stream));
+                     ctx->tmp_covA.as<float4>(), ctx->tmp_covB.as<float4>(), nullptr, nullptr, depth, 0, ctx->stream, ctx->src_has_lo ? ctx->tmp_lo.as<float4>() : nullptr));
   // original order -> the search order of the source (chunk-transposed Morton)
   CU(launch_gather(ctx->src_perm.as<uint32_t>(), n, ctx->tmp_covA.as<float4>(), ctx->src_covA.as<float4>(), ctx->tmp_covB.as<float4>(), ctx->src_covB.as<float4>(),
                    nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream));

@@ -62,6 +62,7 @@ struct sgb_ctx {
   bool tgt_has_normals = false, tgt_has_covs = false;
   bool tgt_is_voxel = false, tgt_ready = false;
   sgb::DevBuf tgt_orig_pts, tgt_orig_normals, tgt_orig_covA, tgt_orig_covB;  // original order
+  sgb::DevBuf tgt_orig_lo, tmp_lo, pre_lo;  // what the FP32 rounding of the coordinates dropped (target / source / scratch cloud, original order): feature estimation only
   sgb::DevBuf tgt_pts, tgt_normals, tgt_covA, tgt_covB;                      // leaf order (or voxel order)
   sgb::DevBuf tgt_nodes, tgt_perm, tgt_pnodes;  // kd nodes (8 B), leaf permutation, packet records (64 B / inner node)
   int tree_depth = 0;
@@ -112,6 +113,7 @@ struct sgb_ctx {
   // ---- preprocessing scratch (sgb_capi_preprocess.cu) ----
   sgb::DevBuf pre_pts, pre_leaf_pts, pre_nodes, pre_perm, pre_centre, pre_bounds, pre_out_normals, pre_out_covs, pre_heads, pre_slots, pre_vals_out;
   sgb::DevBuf pre_vox_coords;  // integer voxel coordinates of sgb_target_build_voxelmap (its own scratch: tmp_pts belongs to the source)
+  bool tgt_has_lo = false, src_has_lo = false;  // tgt_orig_lo / tmp_lo hold the residuals of the current target / source
   bool src_orig_valid = false;  // tmp_pts holds the current source in original order (sgb_source_estimate_features needs it)
   bool tgt_feats_leaf_only = false;  // normals / covariances were estimated on the device into the leaf-ordered streams only
 

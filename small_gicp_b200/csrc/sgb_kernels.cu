@@ -412,13 +412,16 @@ __device__ __forceinline__ uint64_t curve_key(double x, double y, double z, doub
 // raw (double AoS) -> centred float4 in ORIGINAL order (w = index), optional features, optional curve key
 __global__ void convert_kernel(const double4* __restrict__ pts, const double4* __restrict__ normals, const double* __restrict__ covs, size_t n,
                                const double* __restrict__ centre, float4* out_pts, float4* out_normals, float4* out_covA, float4* out_covB,
-                               uint64_t* keys, uint32_t* vals) {
+                               uint64_t* keys, uint32_t* vals, float4* out_lo) {
   const double cx = centre[0], cy = centre[1], cz = centre[2];
   const double inv_ext = 2097151.0 / centre[3];
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const double4 p = pts[i];
     const double x = p.x - cx, y = p.y - cy, z = p.z - cz;
     out_pts[i] = make_float4((float)x, (float)y, (float)z, __int_as_float(static_cast<int>(i)));
+    // what the rounding to FP32 dropped (hi + lo carries ~48 bits of x - c): the feature estimation ranks its neighbour candidates and
+    // sums its covariances on the exact coordinates, so that its neighbour SETS are the reference's, not FP32 near-tie variants of them
+    if (out_lo) out_lo[i] = make_float4((float)(x - (double)(float)x), (float)(y - (double)(float)y), (float)(z - (double)(float)z), 0.f);
     if (normals) {
       const double4 nn = normals[i];
       out_normals[i] = make_float4((float)nn.x, (float)nn.y, (float)nn.z, 0.f);
@@ -695,10 +698,10 @@ cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bound
 }
 
 cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,
-                           float4* out_normals, float4* out_covA, float4* out_covB, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st) {
+                           float4* out_normals, float4* out_covA, float4* out_covB, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st, float4* out_lo) {
   if (!n) return cudaSuccess;
   convert_kernel<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(reinterpret_cast<const double4*>(d_pts4), reinterpret_cast<const double4*>(d_normals4), d_covs16,
-                                                                 n, d_centre4, out_pts, out_normals, out_covA, out_covB, keys, vals);
+                                                                 n, d_centre4, out_pts, out_normals, out_covA, out_covB, keys, vals, out_lo);
   return cudaGetLastError();
 }
 

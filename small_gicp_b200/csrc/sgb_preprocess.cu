@@ -185,31 +185,84 @@ __device__ __forceinline__ void smallest_eigenvector(double a00, double a01, dou
 /// One thread per point of the cloud in LEAF order (neighbouring threads query neighbouring points).
 /// mode bit 0: normals, bit 1: covariances.  Outputs are written in the cloud's ORIGINAL order
 /// (index carried in pts[].w): device layout (float4 streams) and / or the reference's double layout.
+///
+/// Neighbour sets.  The search runs on the centred FP32 coordinates (rounded by up to ~2 um at 50 m), the reference on doubles: at the
+/// k-th neighbour a near-tie could swap one point of the set -- rare (0.5 % of the points), but a different covariance where it happens.
+/// So the search collects k + kFeatExtra candidates, and the k nearest of them are picked by their distance on the EXACT coordinates
+/// (hi + lo, lo = what the FP32 rounding dropped, kept in original order): the set is then the reference's unless two candidates are
+/// equidistant to ~1e-12 m^2, and the covariance sums use the exact coordinates as well.  lo == nullptr: FP32 coordinates throughout.
+constexpr int kFeatExtra = 4;
 template <int KMAX>
 __global__ void __launch_bounds__(kLinBlock) features_kernel(const float4* __restrict__ pnodes, const float4* __restrict__ pts, uint32_t n, int k,
                                                              const double* __restrict__ centre, int mode, float4* out_normals, float4* out_covA,
-                                                             float4* out_covB, double* out_normals_d, double* out_covs_d, int leaf_order_out, int depth) {
+                                                             float4* out_covB, double* out_normals_d, double* out_covs_d, int leaf_order_out, int depth,
+                                                             const float4* __restrict__ lo) {
   extern __shared__ uint2 s_stack[];  // [depth][kLinBlock] descriptors, then [depth][kLinBlock] distances
+  constexpr int KC = KMAX + kFeatExtra;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = __ldg(&pts[i]);
-  KnnList<KMAX> L;
-  L.init(k);
-  bvh_knn<KMAX>(pnodes, pts, q.x, q.y, q.z, L, s_stack, reinterpret_cast<float*>(s_stack + static_cast<size_t>(depth) * kLinBlock));
+  KnnList<KC> L;
+  const int kc = lo ? k + kFeatExtra : k;
+  L.init(kc);
+  bvh_knn<KC>(pnodes, pts, q.x, q.y, q.z, L, s_stack, reinterpret_cast<float*>(s_stack + static_cast<size_t>(depth) * kLinBlock));
+  const uint32_t qo = static_cast<uint32_t>(__float_as_int(q.w));
+  double qx = q.x, qy = q.y, qz = q.z;
+  if (lo) {
+    const float4 l = __ldg(&lo[qo]);
+    qx += l.x; qy += l.y; qz += l.z;
+  }
+  // exact offset of candidate j from the query (hi + lo of both)
+  auto offset = [&](int j, double& x, double& y, double& z) {
+    const float4 t = __ldg(&pts[L.i[j]]);
+    double tx = t.x, ty = t.y, tz = t.z;
+    if (lo) {
+      const float4 l = __ldg(&lo[static_cast<uint32_t>(__float_as_int(t.w))]);
+      tx += l.x; ty += l.y; tz += l.z;
+    }
+    x = tx - qx; y = ty - qy; z = tz - qz;
+  };
+  // exact squared distances of the candidates (-1 = no candidate / dropped)
+  double d2[KC];
   int found = 0;
-  // sums relative to the query point (covariance is translation invariant; keeps the FP64 sums well conditioned)
-  double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int j = 0; j < KMAX; j++) {
-    if (j < k && L.i[j] != kNone) {
-      const float4 t = __ldg(&pts[L.i[j]]);
-      const double x = static_cast<double>(t.x) - q.x, y = static_cast<double>(t.y) - q.y, z = static_cast<double>(t.z) - q.z;
-      s[0] += x; s[1] += y; s[2] += z;
-      ss[0] += x * x; ss[1] += x * y; ss[2] += x * z; ss[3] += y * y; ss[4] += y * z; ss[5] += z * z;
+  for (int j = 0; j < KC; j++) {
+    d2[j] = -1.0;
+    if (j < kc && L.i[j] != kNone) {
+      double x, y, z;
+      offset(j, x, y, z);
+      d2[j] = x * x + y * y + z * z;
       found++;
     }
   }
-  const uint32_t orig = leaf_order_out ? i : static_cast<uint32_t>(__float_as_int(q.w));
+  // drop the (found - k) farthest candidates (exact distances; among exact ties the later arrival goes, knn_result.hpp:88-101)
+  for (int drop = found - k; drop > 0; drop--) {
+    double worst = -1.0;
+    int wj = -1;
+#pragma unroll
+    for (int j = 0; j < KC; j++)
+      if (d2[j] >= worst && d2[j] >= 0.0) {
+        worst = d2[j];
+        wj = j;
+      }
+#pragma unroll
+    for (int j = 0; j < KC; j++)
+      if (j == wj) d2[j] = -1.0;
+    found--;
+  }
+  // sums relative to the query point (covariance is translation invariant; keeps the FP64 sums well conditioned); the offsets are
+  // re-derived rather than kept: 3 x KC doubles of registers would spill
+  double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < KC; j++) {
+    if (d2[j] >= 0.0) {
+      double x, y, z;
+      offset(j, x, y, z);
+      s[0] += x; s[1] += y; s[2] += z;
+      ss[0] += x * x; ss[1] += x * y; ss[2] += x * z; ss[3] += y * y; ss[4] += y * z; ss[5] += z * z;
+    }
+  }
+  const uint32_t orig = leaf_order_out ? i : qo;
   double nrm[3] = {0.0, 0.0, 0.0};
   double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};  // < 5 neighbours: identity covariance, zero normal (normal_estimation.hpp:33-37,71-75)
   if (found >= 5) {
@@ -225,7 +278,7 @@ __global__ void __launch_bounds__(kLinBlock) features_kernel(const float4* __res
     cov[0] = 1.0 - w * v[0] * v[0]; cov[1] = -w * v[0] * v[1]; cov[2] = -w * v[0] * v[2];
     cov[3] = 1.0 - w * v[1] * v[1]; cov[4] = -w * v[1] * v[2]; cov[5] = 1.0 - w * v[2] * v[2];
     // flip the normal toward the origin of the cloud's own frame (normal_estimation.hpp:19-23)
-    const double px = static_cast<double>(q.x) + centre[0], py = static_cast<double>(q.y) + centre[1], pz = static_cast<double>(q.z) + centre[2];
+    const double px = qx + centre[0], py = qy + centre[1], pz = qz + centre[2];
     const double sgn = (px * v[0] + py * v[1] + pz * v[2]) > 0.0 ? -1.0 : 1.0;
     nrm[0] = sgn * v[0]; nrm[1] = sgn * v[1]; nrm[2] = sgn * v[2];
   }
@@ -253,7 +306,7 @@ __global__ void __launch_bounds__(kLinBlock) features_kernel(const float4* __res
 
 template <int KMAX>
 static cudaError_t launch_features_t(const float4* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* on, float4* oa, float4* ob,
-                                     double* ond, double* ocd, int depth, int leaf_order_out, cudaStream_t st) {
+                                     double* ond, double* ocd, int depth, int leaf_order_out, cudaStream_t st, const float4* lo) {
   if (depth < 1) depth = 1;
   const size_t smem = static_cast<size_t>(depth) * kLinBlock * (sizeof(uint2) + sizeof(float));
   if (smem > 48 * 1024) {
@@ -261,16 +314,16 @@ static cudaError_t launch_features_t(const float4* nodes, const float4* pts, uin
     if (e != cudaSuccess) return e;
   }
   const int grid = static_cast<int>((n + kLinBlock - 1) / kLinBlock);
-  features_kernel<KMAX><<<grid, kLinBlock, smem, st>>>(nodes, pts, n, k, centre, mode, on, oa, ob, ond, ocd, leaf_order_out, depth);
+  features_kernel<KMAX><<<grid, kLinBlock, smem, st>>>(nodes, pts, n, k, centre, mode, on, oa, ob, ond, ocd, leaf_order_out, depth, lo);
   return cudaGetLastError();
 }
 
 cudaError_t launch_features(const float4* nodes, const float4* pts, uint32_t n, int k, const double* centre, int mode, float4* out_normals, float4* out_covA,
-                            float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st) {
+                            float4* out_covB, double* out_normals_d, double* out_covs_d, int depth, int leaf_order_out, cudaStream_t st, const float4* lo_orig) {
   if (n == 0) return cudaSuccess;
-  if (k <= 10) return launch_features_t<10>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
-  if (k <= 20) return launch_features_t<20>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
-  if (k <= 32) return launch_features_t<32>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st);
+  if (k <= 10) return launch_features_t<10>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st, lo_orig);
+  if (k <= 20) return launch_features_t<20>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st, lo_orig);
+  if (k <= 32) return launch_features_t<32>(nodes, pts, n, k, centre, mode, out_normals, out_covA, out_covB, out_normals_d, out_covs_d, depth, leaf_order_out, st, lo_orig);
   return cudaErrorInvalidValue;
 }
 

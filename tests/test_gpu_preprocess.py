@@ -61,17 +61,21 @@ def test_features_match_oracle(golden, ctx, k):
     # every sign disagreement to sit on that boundary
     flipped = np.einsum("ij,ij->i", N[:, :3], N0[:, :3]) < 0
     pn = np.abs(np.einsum("ij,ij->i", P[:, :3], N0[:, :3])) / np.linalg.norm(P[:, :3], axis=1)
-    assert flipped.sum() <= 5 and np.all((pn[flipped] < 1e-3) | ~np.isfinite(pn[flipped])), (flipped.sum(), pn[flipped])
+    if flipped.any():
+        j = np.nonzero(flipped)[0][:3]
+        print("sign coin tosses:", int(flipped.sum()), "pn", pn[flipped][:8], "\nP", P[j, :3], "\nN", N[j, :3], "\nN0", N0[j, :3])
+    assert flipped.sum() <= max(5, 0.005 * len(P)) and np.all((pn[flipped] < 1e-6) | ~np.isfinite(pn[flipped])), (flipped.sum(), pn[flipped])
     assert np.isfinite(N0).all(axis=1).mean() > 0.999  # the oracle's closed-form solver may emit NaN on degenerate neighbourhoods
     N0 = np.nan_to_num(N0)
     C0 = np.nan_to_num(C0)
     dn = np.minimum(np.abs(N - N0).max(axis=1), np.abs(N + N0).max(axis=1))
     dc = np.abs(C - C0).reshape(len(P), -1).max(axis=1)
-    ok = (dn < 1e-5) & (dc < 1e-5)
-    assert ok.mean() > 0.995, ok.mean()
-    assert np.median(dn) < 5e-6 and np.median(dc) < 5e-6  # FP32 coordinate storage
-    # the rest: FP32 near-ties at the k-th neighbour swap one neighbour out of k for a few points
-    assert np.quantile(dn, 0.999) < 0.2, np.quantile(dn, 0.999)
+    # The search runs in FP32, but the k nearest are picked -- and the covariance summed -- on the exact coordinates: the neighbour SETS are
+    # the oracle's (no near-tie swaps), what is left is the conditioning of the smallest eigenvector of nearly isotropic neighbourhoods.
+    ok = (dn < 1e-6) & (dc < 1e-6)
+    print("features k=%d: within 1e-6: %.5f, median dn %.2e dc %.2e, max dn %.2e dc %.2e" % (k, ok.mean(), np.median(dn), np.median(dc), dn.max(), dc.max()))
+    assert ok.mean() > 0.999, ok.mean()
+    assert np.median(dn) < 1e-9 and np.median(dc) < 1e-9
 
 
 def test_features_few_points(ctx):

@@ -31,13 +31,11 @@ def test_helper_align_matches_oracle(golden, oracle_pipeline, name, kind, factor
     rot, trans = pose_error(Tgt, r.T_target_source)
     assert rot < np.deg2rad(2.5) and trans < 0.2  # helper_test.cpp:27-39
     rot, trans = pose_error(ref.T_target_source, r.T_target_source)
-    if kind == 0:
-        # ICP uses points only: identical inputs (device voxel grid == oracle's to 1e-9) -> the north-star bar
-        assert rot < 1e-4 and trans < 1e-3, (rot, trans)
-        assert r.iterations == ref.iterations and abs(r.num_inliers - ref.num_inliers) <= 2
-    else:
-        # normals / covariances come from the device k-NN (FP32 near-ties swap a neighbour for a few points)
-        assert rot < 2e-3 and trans < 1e-2, (name, rot, trans)
+    # the north-star bar for every factor: the device voxel grid equals the oracle's to 1e-9, and the device k-NN ranks its candidates
+    # on the exact coordinates, so normals / covariances come from the reference's own neighbour sets
+    print(name, "pose vs oracle:", rot, trans, "iterations", r.iterations, ref.iterations)
+    assert rot < 1e-4 and trans < 1e-3, (name, rot, trans)
+    assert r.iterations == ref.iterations and abs(r.num_inliers - ref.num_inliers) <= 2
 
 
 def test_helper_align_vgicp(golden, oracle_pipeline):
@@ -51,7 +49,8 @@ def test_helper_align_vgicp(golden, oracle_pipeline):
     rot, trans = pose_error(Tgt, r.T_target_source)
     assert rot < np.deg2rad(2.5) and trans < 0.2
     rot, trans = pose_error(ref.T_target_source, r.T_target_source)
-    assert rot < 2e-3 and trans < 1e-2, (rot, trans)
+    print("VGICP pose vs oracle:", rot, trans)
+    assert rot < 1e-4 and trans < 1e-3, (rot, trans)
 
 
 def test_helper_align_empty(golden):
