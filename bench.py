@@ -499,6 +499,8 @@ def run_c5(B, sizes):
             ctx.estimate_target_features(20)
             src = syn.sample_cloud_torch(world_def, n, 44, B.dev, transform=np.linalg.inv(Tgt))
             lo, hi = shard(n, B.rank, B.world)
+            if B.world > 1:  # spatially coherent shards (slabs along x): a rank only touches its part of the replicated target
+                src = src[torch.argsort(src[:, 0])].contiguous()
             if B.world == 1:  # the whole source is this rank's: covariances estimated in place, nothing leaves the library
                 ctx.set_source(src)
                 ctx.estimate_source_features(20)
@@ -534,7 +536,7 @@ def run_c5(B, sizes):
             ctx.close()
             torch.cuda.empty_cache()
     return {
-        "what": "BASELINE configs[4]: linearize (GICP, DistanceRejector(1.0)) over N target x N source points, density constant; ONE source strong-sharded over the GPUs, target + kd-tree + block lists replicated; clouds generated and prepared on the device (kd-tree, k=20 covariances); unseeded search; CUDA events, L2 flushed, max over ranks",
+        "what": "BASELINE configs[4]: linearize (GICP, DistanceRejector(1.0)) over N target x N source points, density constant; ONE source strong-sharded over the GPUs (slabs along x), target + kd-tree + block lists replicated; clouds generated and prepared on the device (kd-tree, k=20 covariances); unseeded search; CUDA events, L2 flushed, max over ranks",
         "n_gpus": B.world,
         "rows": rows,
     }
@@ -557,6 +559,8 @@ def run_c4(B, n):
     n_vox = ctx.target_size
     del tgt, tcov
     src = syn.sample_cloud_torch(world_def, n, 44, B.dev, transform=np.linalg.inv(Tgt))
+    if B.world > 1:  # spatially coherent shards (slabs along x)
+        src = src[torch.argsort(src[:, 0])].contiguous()
     _, scov = ctx.estimate_features(src, 20, normals=False)
     lo, hi = shard(n, B.rank, B.world)
     ctx.set_source(src[lo:hi].contiguous(), scov[lo:hi].contiguous())
@@ -655,7 +659,7 @@ def run_c3(B, n_frames):
     frames = [syn.lidar_frame_torch(world_def, poses[f], 45 + f, B.dev).cpu().numpy() for f in range(n_frames)]
     torch.cuda.synchronize()
     ctx, _ = B.context()
-    stages = {"voxelgrid_ms": [], "source_upload_covariances_ms": [], "target_tree_grid_covariances_ms": [], "lm_align_ms": [], "total_ms": []}
+    stages = {"voxelgrid_ms": [], "source_upload_tree_covariances_ms": [], "lm_align_ms": [], "handover_to_target_grid_ms": [], "total_ms": []}
     lm_stats, n_down, errs = [], [], []
     prev = None
     T_est, T_gt_acc = np.eye(4), np.eye(4)
@@ -669,10 +673,10 @@ def run_c3(B, n_frames):
         pts = ctx.voxelgrid_sampling(frames[f], 0.25)
         t1 = clock()
         n_down.append(len(pts))
+        ctx.set_source(pts)
+        ctx.estimate_source_features(20)  # builds the frame's kd-tree on the device and keeps it
+        t2 = clock()
         if prev is not None:
-            ctx.set_source(pts)
-            ctx.estimate_source_features(20)
-            t2 = clock()
             T, its, conv, n_lin, n_err = lm_align(lambda T: ctx.linearize(T, factor=sg.FACTOR_GICP, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0), ctx.error)
             t3 = clock()
             lm_stats.append((its + 1, n_lin, n_err))
@@ -680,23 +684,22 @@ def run_c3(B, n_frames):
             errs.append(pose_error(gt, T))
             T_est, T_gt_acc = T_est @ T, T_gt_acc @ gt
         else:
-            t2 = t3 = t1
-        # this frame becomes the next target: tree + block lists + normals / covariances, all on the device
-        ctx.set_target(pts)
-        ctx.build_target_kdtree(0)
-        ctx.estimate_target_features(20)
+            t3 = t2
+        # this frame is the next target (odometry_benchmark_small_gicp_tbb.cpp:41-43): points, tree and covariances are taken over on the
+        # device, only the grid front end is built on top
+        ctx.adopt_source_as_target()
         t4 = clock()
         if prev is not None and f >= 2:  # frame 1 pays lazy module loading / first allocations
             stages["voxelgrid_ms"].append((t1 - t0) * 1e3)
-            stages["source_upload_covariances_ms"].append((t2 - t1) * 1e3)
+            stages["source_upload_tree_covariances_ms"].append((t2 - t1) * 1e3)
             stages["lm_align_ms"].append((t3 - t2) * 1e3)
-            stages["target_tree_grid_covariances_ms"].append((t4 - t3) * 1e3)
+            stages["handover_to_target_grid_ms"].append((t4 - t3) * 1e3)
             stages["total_ms"].append((t4 - t0) * 1e3)
         prev = pts
     ctx.close()
     rot_acc, trans_acc = pose_error(T_gt_acc, T_est)
     res = {
-        "what": "BASELINE configs[2]: synthetic 64-beam x 1875-azimuth LiDAR stream (120k rays / frame, sensor moving 1.0 m + 1 deg yaw per frame, range noise 0.02 m) in the 400 m room; per frame 0.25 m voxel grid, kd-tree + grid, k=20 covariances, LevenbergMarquardt GICP vs the previous frame from identity; host-resident input frames, wall clock per stage (synchronised), frames 2.. averaged",
+        "what": "BASELINE configs[2]: synthetic 64-beam x 1875-azimuth LiDAR stream (120k rays / frame, sensor moving 1.0 m + 1 deg yaw per frame, range noise 0.02 m) in the 400 m room; per frame 0.25 m voxel grid, kd-tree, k=20 covariances, LevenbergMarquardt GICP vs the previous frame from identity, then the frame is handed over as the next target (sgb_target_adopt_source: tree and covariances reused as the reference's loop reuses them, grid front end built); host-resident input frames, wall clock per stage (synchronised), frames 2.. averaged",
         "frames": n_frames,
         "points_per_frame_raw": int(np.mean([len(x) for x in frames])),
         "points_per_frame_downsampled": int(np.mean(n_down)),
@@ -998,12 +1001,14 @@ def run_ours(args):
         barrier()
         if fused:
             ctx.comm_disconnect()
-        if world == 1:
+        if world == 1 and args.c3_frames > 1:
             try:
                 extras["c3"] = run_c3(B, args.c3_frames)
             except Exception as e:
                 extras["c3"] = {"error": repr(e)}
         for key, fn in (("c4", lambda: run_c4(B, args.c4_points)), ("c5", lambda: run_c5(B, [int(x) for x in args.c5_sizes.split(",") if x]))):
+            if key == "c4" and args.c4_points <= 0:
+                continue
             try:
                 extras[key] = fn()
             except Exception as e:  # every rank raises or none: the legs are collective

@@ -172,6 +172,11 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points_xyz1, int
  * odometry_benchmark_small_gicp_tbb.cpp:26-27). */
 int sgb_target_estimate_features(sgb_ctx* ctx, int num_neighbors);
 int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors);
+/* Frame streams (odometry_benchmark_small_gicp_tbb.cpp:41-43: `target_points = points; target_tree = tree;`): the CURRENT SOURCE becomes the
+ * target -- its points, the kd-tree sgb_source_estimate_features built over them and its covariances are taken over on the device (a tree
+ * is built only if none exists; host-supplied covariances are taken over too), the grid front end is built, and the context has no source
+ * until the next sgb_source_set_points.  No normals: call sgb_target_estimate_features for point-to-plane. */
+int sgb_target_adopt_source(sgb_ctx* ctx);
 /* replaces voxelgrid_sampling{,_omp,_tbb} (include/small_gicp/util/downsampling.hpp:22-78): one output point per occupied
  * voxel = mean of its points, voxels ordered by the reference's 63-bit key (x | y<<21 | z<<42 of floor(p/leaf)+2^20);
  * points whose voxel coordinate leaves the 21-bit range are dropped.  out_points_xyz1 must hold n points. */

@@ -52,7 +52,7 @@ def main():
     r = json.load(open(os.path.join(src, "bench_ref.json")))
     L = []
     L.append(f"# {os.path.basename(dst)}/{tag} -- the four launches of `sgb_linearize` (1M x 1M synthetic GICP), ncu --set full\n")
-    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|pending_search|packet_search|factor_reduce" -s 32 -c 20 python bench.py --steps 20 --warmup 3 --no-cpu-baseline` with `SGB_BENCH_ROLL=5` (`scripts/gpu_ncu.sh`)')
+    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|pending_search|packet_search|factor_reduce" -s 60 -c 20 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras` with `SGB_BENCH_ROLL=5` (`scripts/gpu_ncu.sh`)')
     L.append(f"(k=20 covariances, L2 flushed between steps; the captured launches are one pass over the {len(groups)} poses of the Gauss-Newton trajectory: {len(conv)} converged, {len(mis)} misaligned).")
     L.append("Which search kernel does the work is decided on the device from the probe's pending counter; the other one exits at once.\n")
     L.append(f"## Converged poses -- mean of {len(conv)} linearizes\n")

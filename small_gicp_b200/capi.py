@@ -53,6 +53,7 @@ _SIGNATURES = {
     "sgb_estimate_features": (C.c_int, [_vp, C.c_size_t, _dp, C.c_int, _dp, _dp]),
     "sgb_target_estimate_features": (C.c_int, [_vp, C.c_int]),
     "sgb_source_estimate_features": (C.c_int, [_vp, C.c_int]),
+    "sgb_target_adopt_source": (C.c_int, [_vp]),
     "sgb_voxelgrid_sampling": (C.c_int, [_vp, C.c_size_t, _dp, C.c_double, _dp, C.POINTER(C.c_size_t)]),
 }
 
@@ -329,6 +330,10 @@ class Context:
 
     def estimate_source_features(self, num_neighbors=20):
         self._check(self._L.sgb_source_estimate_features(self._h, int(num_neighbors)))
+
+    def adopt_source_as_target(self):
+        """frame streams: the current source (points, its device-built tree, covariances) becomes the target; no source afterwards"""
+        self._check(self._L.sgb_target_adopt_source(self._h))
 
     def voxelgrid_sampling(self, points, leaf_size):
         """voxelgrid_sampling (util/downsampling.hpp:22-78): returns the (M,4) down-sampled points"""

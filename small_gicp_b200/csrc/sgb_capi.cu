@@ -443,6 +443,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_PROBE_TAIL")) ctx->probe_batch_tail = (s[0] == '1');        // 1 = probe scans its list in clamped batches of eight (A/B, sgb_grid.cu)
   if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
   if (const char* s = getenv("SGB_CHUNK_CLASSES")) ctx->use_chunk_classes = !(s[0] == '0');  // 0 = no work lists by cost class: chunks in curve order
+  if (const char* s = getenv("SGB_GRID_ORDER")) ctx->grid_curve_order = !(s[0] == '0');  // 0 = block lists in raster order of the packed block coordinates
   if (const char* s = getenv("SGB_TMA_LEAF")) ctx->tma_leaf = (s[0] == '1');  // 1 = dense leaf scans read a cp.async.bulk (TMA) staged copy of the leaf
   if (const char* s = getenv("SGB_CLASS_FALLBACK_PCT")) ctx->class_fallback_pct = static_cast<uint32_t>(std::max(0, atoi(s)));
   if (const char* s = getenv("SGB_CLASS_WIDE")) ctx->class_wide_cells = static_cast<float>(atof(s));
@@ -811,6 +812,7 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
   ctx->have_lin = false;
   ctx->corr_seeds = false;
   ctx->src_orig_valid = n > 0;  // tmp_pts (filled below) holds this source in original order
+  ctx->src_tree_valid = ctx->src_cov_orig_valid = false;
   CU(ctx->src_centre.reserve(4 * sizeof(double)));
   CU(ctx->src_bounds.reserve(6 * sizeof(double)));
   if (n == 0) return 0;

@@ -43,6 +43,8 @@ int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d
                         perm.as<uint32_t>(), n, ctx->stream));
   CU(launch_gather(perm.as<uint32_t>(), n, d_orig_pts, leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream));
   ctx->launches += 5;
+  // (Skipping this refinement for small clouds -- its d radix sorts are pure launch latency at 15k points -- was measured and rejected:
+  // the k = 20 searches of the covariance estimation in the unrefined tree cost more than the sorts save, r02j: 6.8 vs 4.1 ms per frame.)
   if (ctx->tree_quality >= 1) {
     // median-split refinement: level by level, sort every node's points along the widest axis of its box; the balanced
     // position boundaries of the next level are then exactly the median splits of a kd-tree (same quality as the host
@@ -117,7 +119,7 @@ int build_grid(sgb_ctx* ctx) {
   uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the two pending counters double as scratch during construction
   uint32_t* d_max_list = d_distinct + 1;
   CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, blocks, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
-                      ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->stream));
+                      ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->grid_curve_order, ctx->stream));
   uint32_t distinct = 0;
   CU(cudaMemcpyAsync(&distinct, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -125,7 +127,7 @@ int build_grid(sgb_ctx* ctx) {
   while (capacity < 2ull * distinct) capacity <<= 1;  // load factor <= 1/2
   CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
   CU(launch_grid_fill(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n_ent),
-                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, d_max_list, ctx->stream));
+                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, d_max_list, ctx->grid_curve_order, ctx->stream));
   ctx->grid_blocks = blocks;
   ctx->pending_clean = false;  // d_distinct / d_max_list live in the pending counters
   ctx->launches += 9;
@@ -165,6 +167,7 @@ int sgb_estimate_features(sgb_ctx* ctx, size_t n, const double* points, int num_
                     nullptr, ctx->sm_count, ctx->stream, ctx->pre_lo.as<float4>()));
   ctx->launches += 4;
   int depth = 0;
+  ctx->src_tree_valid = false;  // the scratch tree buffers are about to hold THIS cloud's tree
   if (int rc = build_lbvh(ctx, ctx->pre_pts.as<float4>(), n, ctx->pre_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
   if (out_normals) CU(ctx->pre_out_normals.reserve(n * 4 * sizeof(double)));
   if (out_covs) CU(ctx->pre_out_covs.reserve(n * 16 * sizeof(double)));
@@ -219,7 +222,11 @@ int sgb_source_estimate_features(sgb_ctx* ctx, int num_neighbors) {
   // tmp_pts still holds the source in ORIGINAL order (centred FP32, w = index) from sgb_source_set_points
   if (!ctx->src_orig_valid) return fail(ctx, 1, "sgb_source_estimate_features: no source points (call sgb_source_set_points first)");
   int depth = 0;
+  ctx->src_tree_valid = false;
   if (int rc = build_lbvh(ctx, ctx->tmp_pts.as<float4>(), n, ctx->src_centre.as<double>(), ctx->pre_perm, ctx->pre_leaf_pts, ctx->pre_nodes, &depth)) return rc;
+  ctx->src_tree_valid = true;  // kept: sgb_target_adopt_source turns this cloud, tree and covariances into the next target
+  ctx->src_tree_depth = depth;
+  ctx->src_cov_orig_valid = true;
   CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
   CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
   CU(ctx->src_covA.reserve(n * sizeof(float4)));
@@ -274,6 +281,67 @@ int sgb_voxelgrid_sampling(sgb_ctx* ctx, size_t n, const double* points, double 
   }
   *n_out = count;
   return 0;
+}
+
+// The frame-stream hand-over (odometry_benchmark_small_gicp_tbb.cpp:41-43: `target_points = points; target_tree = tree;`): the cloud that was
+// the source of this align() is the target of the next one.  Everything that already exists on the device is taken over, not rebuilt.
+int sgb_target_adopt_source(sgb_ctx* ctx) {
+  if (!ctx) return 1;
+  if (!ctx->src_orig_valid || ctx->n_src == 0) return fail(ctx, 1, "sgb_target_adopt_source: no source points (call sgb_source_set_points first)");
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n_src;
+  const bool covs = ctx->src_has_covs;
+  // covariances in ORIGINAL order: either still there from the device-side estimation, or un-permuted from the search-ordered streams
+  if (covs && !ctx->src_cov_orig_valid) {
+    CU(ctx->tmp_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tmp_covB.reserve(n * sizeof(float4)));
+    CU(launch_scatter(ctx->src_perm.as<uint32_t>(), n, ctx->src_covA.as<float4>(), ctx->tmp_covA.as<float4>(), ctx->src_covB.as<float4>(), ctx->tmp_covB.as<float4>(),
+                      nullptr, nullptr, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+  }
+  ctx->tgt_orig_pts.swap(ctx->tmp_pts);
+  ctx->tgt_has_lo = ctx->src_has_lo;
+  if (ctx->src_has_lo) ctx->tgt_orig_lo.swap(ctx->tmp_lo);
+  if (covs) {
+    ctx->tgt_orig_covA.swap(ctx->tmp_covA);
+    ctx->tgt_orig_covB.swap(ctx->tmp_covB);
+  }
+  ctx->tgt_centre.swap(ctx->src_centre);
+  ctx->tgt_bounds.swap(ctx->src_bounds);
+  CU(ctx->src_centre.reserve(4 * sizeof(double)));
+  CU(ctx->src_bounds.reserve(6 * sizeof(double)));
+  ctx->n_tgt = n;
+  ctx->tgt_has_normals = false;
+  ctx->tgt_has_covs = covs;
+  ctx->tgt_is_voxel = false;
+  ctx->tgt_has_kd = false;
+  ctx->tgt_feats_leaf_only = false;
+  ctx->grid_ready = false;
+  ctx->have_lin = false;
+  ctx->corr_seeds = false;
+  int depth = ctx->src_tree_depth;
+  if (ctx->src_tree_valid) {
+    ctx->tgt_perm.swap(ctx->pre_perm);
+    ctx->tgt_pts.swap(ctx->pre_leaf_pts);
+    ctx->tgt_pnodes.swap(ctx->pre_nodes);
+  } else if (int rc = build_lbvh(ctx, ctx->tgt_orig_pts.as<float4>(), n, ctx->tgt_centre.as<double>(), ctx->tgt_perm, ctx->tgt_pts, ctx->tgt_pnodes, &depth)) {
+    return rc;
+  }
+  if (depth > 40) return fail(ctx, 1, "sgb_target_adopt_source: tree too deep");
+  if (covs) {
+    CU(ctx->tgt_covA.reserve(n * sizeof(float4)));
+    CU(ctx->tgt_covB.reserve(n * sizeof(float4)));
+    CU(launch_gather(ctx->tgt_perm.as<uint32_t>(), n, nullptr, nullptr, nullptr, nullptr, ctx->tgt_orig_covA.as<float4>(), ctx->tgt_covA.as<float4>(),
+                     ctx->tgt_orig_covB.as<float4>(), ctx->tgt_covB.as<float4>(), ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+  }
+  ctx->tree_depth = depth;
+  ctx->n_pnodes = (static_cast<size_t>(1) << (depth - 1)) - 1;
+  ctx->tgt_ready = true;
+  // the context has no source until the next sgb_source_set_points (its buffers now belong to the target)
+  ctx->n_src = 0;
+  ctx->src_has_covs = ctx->src_orig_valid = ctx->src_tree_valid = ctx->src_cov_orig_valid = ctx->src_has_lo = false;
+  return build_grid(ctx);
 }
 
 // Gaussian voxel map built on the device: replaces IncrementalVoxelMap<GaussianVoxel>::insert

@@ -36,6 +36,14 @@ struct DevBuf {
   T* as() const {
     return static_cast<T*>(p);
   }
+  void swap(DevBuf& o) {
+    void* tp = p;
+    p = o.p;
+    o.p = tp;
+    const size_t tc = cap;
+    cap = o.cap;
+    o.cap = tc;
+  }
 };
 
 }  // namespace sgb
@@ -85,6 +93,7 @@ struct sgb_ctx {
   bool chunk_lists_clean = false;
   uint32_t class_fallback_pct = 85;  // more than this share of the chunks listed (pending lanes almost everywhere): curve order instead of the lists
   float class_wide_cells = 2.0f;     // search radius (in cells) from which a chunk counts as wide
+  bool grid_curve_order = true;  // block lists laid out along a Morton curve (profiling switch SGB_GRID_ORDER=0: raster order of the packed coordinates)
   bool tma_leaf = false;         // profiling switch SGB_TMA_LEAF=1 (A/B of the north-star's TMA leaf staging)
   bool use_chunk_classes = true; // profiling switch SGB_CHUNK_CLASSES=0: the packet search scans all chunks in curve order
   int packet_parity = 0;
@@ -114,6 +123,9 @@ struct sgb_ctx {
   sgb::DevBuf pre_pts, pre_leaf_pts, pre_nodes, pre_perm, pre_centre, pre_bounds, pre_out_normals, pre_out_covs, pre_heads, pre_slots, pre_vals_out;
   sgb::DevBuf pre_vox_coords;  // integer voxel coordinates of sgb_target_build_voxelmap (its own scratch: tmp_pts belongs to the source)
   bool tgt_has_lo = false, src_has_lo = false;  // tgt_orig_lo / tmp_lo hold the residuals of the current target / source
+  bool src_tree_valid = false;  // pre_perm / pre_leaf_pts / pre_nodes hold the SOURCE's tree (sgb_source_estimate_features built it), depth src_tree_depth
+  bool src_cov_orig_valid = false;  // tmp_covA / tmp_covB hold the source's covariances in original order (estimated on the device)
+  int src_tree_depth = 0;
   bool src_orig_valid = false;  // tmp_pts holds the current source in original order (sgb_source_estimate_features needs it)
   bool tgt_feats_leaf_only = false;  // normals / covariances were estimated on the device into the leaf-ordered streams only
 

@@ -228,12 +228,34 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
   __shared__ double s_red[kLinBlock / 32][NACC];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (NACC > 4) {
+    // Transposing butterfly: at every step a lane keeps one half of the values it still owns and hands the other half to its partner,
+    // so the 32 lanes end up with ONE fully reduced accumulator each (lane l holds sum l): 16 + 8 + 4 + 2 + 1 = 31 exchanges instead of
+    // 5 per accumulator (145 for the 29 sums of linearize -- 9 % of the factor kernel's instructions, profiles/r01/an).  The order of
+    // the additions is fixed by the lane numbers: deterministic.
+    double v[32];
 #pragma unroll
-  for (int k = 0; k < NACC; k++) {
-    double v = acc[k];
+    for (int k = 0; k < 32; k++) v[k] = k < NACC ? acc[k] : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[warp][k] = v;
+    for (int w = 16; w >= 1; w >>= 1) {
+      const bool upper = (lane & w) != 0;
+#pragma unroll
+      for (int k = 0; k < w; k++) {
+        if (k >= NACC) continue;  // both halves are padding
+        const double keep = upper ? v[k + w] : v[k];
+        const double send = upper ? v[k] : v[k + w];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+      }
+    }
+    if (lane < NACC) s_red[warp][lane] = v[0];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NACC; k++) {
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][k] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < NACC) {

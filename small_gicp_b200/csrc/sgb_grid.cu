@@ -45,18 +45,51 @@ __device__ __forceinline__ uint32_t grid_hash_of_key(uint64_t k) {
   return grid_hash(ix, iy, iz);
 }
 
+// Morton (Z-order) code of the three 21-bit offset coordinates: the ORDER in which the lists are laid out in memory.  The table is keyed
+// by the plain packed coordinates (grid_key); only the sort uses the curve, so that the lists a warp of Hilbert-ordered queries needs --
+// a compact patch of ~11 neighbouring blocks -- are neighbours in memory too (DRAM pages, L2 sectors, TLB) instead of being strung along
+// x only (profiles/r02: probe and the 10M - 100M sizes).
+__device__ __forceinline__ uint64_t grid_spread21(uint64_t x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ uint64_t grid_compact21(uint64_t x) {
+  x &= 0x1249249249249249ull;
+  x = (x | x >> 2) & 0x10c30c30c30c30c3ull;
+  x = (x | x >> 4) & 0x100f00f00f00f00full;
+  x = (x | x >> 8) & 0x1f0000ff0000ffull;
+  x = (x | x >> 16) & 0x1f00000000ffffull;
+  x = (x | x >> 32) & 0x1fffffull;
+  return x;
+}
+__device__ __forceinline__ uint64_t grid_order_key(int ix, int iy, int iz, bool curve) {
+  if (!curve) return grid_key(ix, iy, iz);
+  return grid_spread21(static_cast<uint32_t>(ix + (1 << 20))) | (grid_spread21(static_cast<uint32_t>(iy + (1 << 20))) << 1) |
+         (grid_spread21(static_cast<uint32_t>(iz + (1 << 20))) << 2);
+}
+/// sort key -> table key (packed coordinates)
+__device__ __forceinline__ uint64_t grid_table_key(uint64_t k, bool curve) {
+  if (!curve) return k;
+  return grid_compact21(k) | (grid_compact21(k >> 1) << 21) | (grid_compact21(k >> 2) << 42);
+}
+
 // cell key of every target point (leaf-ordered, centred FP32); value = leaf position.
 // BLOCKS: every point is entered under the eight 2 x 2 x 2 cell blocks that contain its cell (block anchor = lowest cell),
 // so that a query finds every point of the block around it in ONE contiguous run (8x the points, one lookup, one loop).
 template <bool BLOCKS>
-__global__ void grid_keys_kernel(const float4* __restrict__ pts, uint32_t n, GridParams g, uint64_t* keys, uint32_t* vals) {
+__global__ void grid_keys_kernel(const float4* __restrict__ pts, uint32_t n, GridParams g, uint64_t* keys, uint32_t* vals, bool curve) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = BLOCKS ? t >> 3 : t, o = BLOCKS ? t & 7u : 0u;
   if (i >= n) return;
   const float4 p = pts[i];
   const int ix = __float2int_rd((p.x - g.origin[0]) * g.inv_cell), iy = __float2int_rd((p.y - g.origin[1]) * g.inv_cell),
             iz = __float2int_rd((p.z - g.origin[2]) * g.inv_cell);
-  keys[t] = grid_key(ix - static_cast<int>(o & 1u), iy - static_cast<int>((o >> 1) & 1u), iz - static_cast<int>(o >> 2));
+  keys[t] = grid_order_key(ix - static_cast<int>(o & 1u), iy - static_cast<int>((o >> 1) & 1u), iz - static_cast<int>(o >> 2), curve);
   vals[t] = i;
 }
 
@@ -70,7 +103,7 @@ __global__ void grid_count_heads_kernel(const uint64_t* __restrict__ keys, uint3
 
 // after the sort: gather the points into cell order (w = leaf position) and insert one table entry per run of equal keys
 __global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ leaf_pos, const float4* __restrict__ leaf_pts, uint32_t n,
-                                 float4* grid_pts, GridSlot* table, uint32_t mask, uint32_t* max_count) {
+                                 float4* grid_pts, GridSlot* table, uint32_t mask, uint32_t* max_count, bool curve) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t lp = leaf_pos[i];
@@ -80,9 +113,10 @@ __global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32
   if (i == 0 || keys[i - 1] != k) {  // head of a cell: count its points, claim a slot
     uint32_t cnt = 1;
     while (i + cnt < n && keys[i + cnt] == k) cnt++;
-    uint32_t slot = grid_hash_of_key(k) & mask;
+    const uint64_t tk = grid_table_key(k, curve);
+    uint32_t slot = grid_hash_of_key(tk) & mask;
     for (;;) {
-      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), ~0ull, static_cast<unsigned long long>(k));
+      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), ~0ull, static_cast<unsigned long long>(tk));
       if (prev == ~0ull) break;
       slot = (slot + 1u) & mask;
     }
@@ -569,12 +603,12 @@ cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* o
 }
 
 cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
-                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, cudaStream_t st) {
+                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, bool curve, cudaStream_t st) {
   const uint32_t m = blocks ? n * 8u : n;
   if (blocks)
-    grid_keys_kernel<true><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in);
+    grid_keys_kernel<true><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in, curve);
   else
-    grid_keys_kernel<false><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in);
+    grid_keys_kernel<false><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in, curve);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(m), 0, 63, st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(d_distinct, 0, sizeof(uint32_t), st);
@@ -584,11 +618,11 @@ cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParam
 }
 
 cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
-                             uint32_t capacity, uint32_t* d_max_count, cudaStream_t st) {
+                             uint32_t capacity, uint32_t* d_max_count, bool curve, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(d_max_count, 0, sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
   grid_table_init_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
-  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u, d_max_count);
+  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u, d_max_count, curve);
   return cudaGetLastError();
 }
 

@@ -91,9 +91,9 @@ struct __align__(16) GridSlot {
 };
 cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* out, cudaStream_t st);
 cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
-                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, cudaStream_t st);
+                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, bool curve, cudaStream_t st);
 cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
-                             uint32_t capacity, uint32_t* d_max_count, cudaStream_t st);
+                             uint32_t capacity, uint32_t* d_max_count, bool curve, cudaStream_t st);
 /// longest list (points) the grid front end accepts: beyond it a single query's scan would dominate (a cluster of near-duplicate
 /// points, or a few far outliers stretching the box so that the cell-count bound inflates the cell) and the exact tree search alone is used
 constexpr uint32_t kGridMaxList = 2048;

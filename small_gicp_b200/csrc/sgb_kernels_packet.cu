@@ -24,6 +24,9 @@ constexpr int kPktWarps = kLinBlock / 32;
 // a leaf wanted by more lanes than this is scanned by all lanes (10 instr / point); otherwise the interested lanes are
 // served one by one by the whole warp (~16 instr / lane): break-even ~ points_per_leaf * 10 / 16
 constexpr int kPacketDenseLanes = 18;
+// resident CTAs per SM the kernel is compiled for: the compiler's own 48 registers -> 10 CTAs x 4 warps.  Forcing 12 (40 registers, 8 B
+// of spills) measured slower (r02j: 0.2444 vs 0.2393 ms at the identity pose, 0.184 vs 0.180 ms at T1).
+constexpr int kPacketCtas = 10;
 
 __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
   const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
@@ -61,8 +64,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   }
 }
 
-template <bool TMA_LEAF>
-__global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
+template <bool TMA_LEAF, int MIN_CTAS>
+__global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
                                                                   const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
                                                                   uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, ChunkClasses cc) {
   // Work distribution: chunks (32 consecutive queries) differ wildly in cost -- all lanes settled by the grid probe, or 32
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kLinBlock) packet_search_kernel(const __grid_c
 int packet_occupancy(int max_depth) {
   int nb = 0;
   const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel<false>, kLinBlock, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel<false, kPacketCtas>, kLinBlock, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
@@ -286,18 +289,22 @@ cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int g
 #ifdef SGB_PROFILING
   if (tma_leaf) {  // A/B (SGB_TMA_LEAF=1): leaf blocks staged by cp.async.bulk + mbarrier
     if (!settled) {
-      packet_search_kernel<true><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+      packet_search_kernel<true, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
       return cudaGetLastError();
     }
-    return launch_dependent(packet_search_kernel<true>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+    return launch_dependent(packet_search_kernel<true, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
   }
 #endif
+#ifdef SGB_PROFILING
+  static const bool twelve = std::getenv("SGB_PACKET_CTAS") && std::atoi(std::getenv("SGB_PACKET_CTAS")) == 12;  // A/B: 40 registers, 12 CTAs / SM
+  if (twelve && settled) return launch_dependent(packet_search_kernel<false, 12>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+#endif
   if (!settled) {  // no grid front end: nothing on the stream this launch could overlap with
-    packet_search_kernel<false><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+    packet_search_kernel<false, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
     return cudaGetLastError();
   }
   (void)tma_leaf;
-  return launch_dependent(packet_search_kernel<false>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+  return launch_dependent(packet_search_kernel<false, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
 }
 
 }  // namespace sgb

@@ -215,3 +215,50 @@ def test_device_features_follow_a_tree_rebuild(golden):
         H, b, e = a.linearize(T, factor=f)
         assert np.linalg.norm(H - H0) <= 1e-6 * np.linalg.norm(H0) and abs(e - e0) <= 1e-6 * e0, f
     a.close()
+
+
+def test_adopting_the_source_equals_setting_the_target(golden):
+    """sgb_target_adopt_source (frame streams): the source -- points, the tree its covariance estimation built, the covariances --
+    becomes the target without a rebuild.  The next frame's sums must equal those against an explicitly set + built + estimated target,
+    both for device-estimated and for host-supplied source covariances."""
+    import small_gicp_b200 as sg
+
+    tgt, src, T = golden
+    a, b = sg.Context(0), sg.Context(0)
+    f0 = a.voxelgrid_sampling(tgt, 0.25)
+    f1 = a.voxelgrid_sampling(src, 0.25)
+    # explicit
+    b.set_target(f0)
+    b.build_target_kdtree()
+    b.estimate_target_features(20)
+    b.set_source(f1)
+    b.estimate_source_features(20)
+    ref = b.linearize(T, factor=sg.FACTOR_GICP)
+    ref_c = b.correspondences()
+    # adopted: device-estimated covariances + the tree that estimation built
+    a.set_source(f0)
+    a.estimate_source_features(20)
+    a.adopt_source_as_target()
+    assert a.source_size == 0 and a.target_size == len(f0)
+    a.set_source(f1)
+    a.estimate_source_features(20)
+    H, b_, e = a.linearize(T, factor=sg.FACTOR_GICP)
+    assert np.linalg.norm(H - ref[0]) <= 1e-6 * np.linalg.norm(ref[0]) and abs(e - ref[2]) <= 1e-6 * ref[2]
+    assert (a.correspondences() != ref_c).sum() <= 2
+    with pytest.raises(sg.SgbError):  # no normals were handed over: point-to-plane says so instead of using stale ones
+        a.linearize(T, factor=sg.FACTOR_PLANE_ICP)
+    a.estimate_target_features(20)
+    a.linearize(T, factor=sg.FACTOR_PLANE_ICP)
+    # adopted: covariances that came from the host, no tree yet
+    _, c0 = b.estimate_features(f0, 20, normals=False)
+    a.set_source(f0, c0)
+    a.adopt_source_as_target()
+    a.set_source(f1)
+    a.estimate_source_features(20)
+    H2, _, e2 = a.linearize(T, factor=sg.FACTOR_GICP)
+    assert np.linalg.norm(H2 - ref[0]) <= 1e-5 * np.linalg.norm(ref[0]) and abs(e2 - ref[2]) <= 1e-5 * ref[2]
+    with pytest.raises(sg.SgbError):
+        a.adopt_source_as_target()
+        a.adopt_source_as_target()  # nothing left to adopt
+    a.close()
+    b.close()
