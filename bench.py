@@ -17,6 +17,7 @@ seeded by its predecessor.  Metric: Mpoints/s per iteration = source points of a
 `cpu_baseline` / --impl reference: the reference's own ParallelReductionOMP<GICPFactor> (oracle/_ref) on this box's host cores.
 Extras on the same line (the other BASELINE configs on hardware; skipped with --no-extras):
 `error_ms`     Reduction::error (LM inner loop) over the same 1M points per GPU.
+`c1`           configs[0]: the bundled PLY pair, ICP, helper align() vs the 1-thread CPU pipeline; per-call latency (N = 1 only).
 `c3`           configs[2]: 120k-ray LiDAR stream, per frame voxel grid / tree + grid / covariances / LM align (N = 1 only).
 `c4`           configs[3]: 10M-point VGICP, LevenbergMarquardt, ONE source strong-sharded over the N GPUs.
 `c5`           configs[4]: linearize over 100k .. 100M points (ONE cloud pair, source strong-sharded over the N GPUs).
@@ -735,6 +736,74 @@ def run_c3(B, n_frames):
     return res
 
 
+def run_c1(B):
+    """configs[0]: the reference's bundled data/target.ply <-> data/source.ply (committed as tests/golden/*_xyz.f32), point-to-point ICP
+    through the helper align() surface (registration_helper.cpp:58-115: 0.25 m voxel grid, k = 10 normals + covariances, kd-tree, LM,
+    <= 20 iterations, 1 m): the C++ host mirror with every stage on the device, wall clock, next to the CPU oracle's restatement of the
+    same pipeline on ONE thread (the configuration BASELINE.json names), and the per-call latency of sgb_linearize at that size."""
+    import oracle as O
+    from small_gicp_b200 import host_api
+
+    sg = B.sg
+    gold = os.path.join(ROOT, "tests", "golden")
+    tgt = np.fromfile(os.path.join(gold, "target_xyz.f32"), dtype="<f4").reshape(-1, 3).astype(np.float64)
+    src = np.fromfile(os.path.join(gold, "source_xyz.f32"), dtype="<f4").reshape(-1, 3).astype(np.float64)
+    T_file = np.loadtxt(os.path.join(gold, "T_target_source.txt")).reshape(4, 4)
+    for _ in range(2):
+        r = host_api.helper_align(tgt, src, type=0)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = host_api.helper_align(tgt, src, type=0)
+    gpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    tp0 = time.perf_counter()
+    tc, tt = O.preprocess_points(tgt, 0.25, 10, 1)
+    sc, st = O.preprocess_points(src, 0.25, 10, 1)
+    t1 = time.perf_counter()
+    ref = O.Registration(factor=O.FACTOR_ICP, num_threads=1).align(tc, tt, sc, np.eye(4))
+    t2 = time.perf_counter()
+    cpu_pre_ms, cpu_total_ms = (t1 - tp0) * 1e3, (t2 - tp0) * 1e3
+    rot, trans = pose_error(ref.T_target_source, r.T_target_source)
+    rot_f, trans_f = pose_error(T_file, r.T_target_source)
+    # per-call latency of the hot path at this size (host-returning sgb_linearize / sgb_error: launch + mapped result + one synchronisation)
+    ctx, _ = B.context()
+    ctx.set_target(tc.points)
+    ctx.build_target_kdtree(0)
+    ctx.set_source(sc.points)
+    T = r.T_target_source
+    for _ in range(20):
+        ctx.linearize(T, factor=sg.FACTOR_ICP)
+        ctx.error(T)
+    n_calls = 200
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        ctx.linearize(T, factor=sg.FACTOR_ICP)
+    lin_us = (time.perf_counter() - t0) * 1e6 / n_calls
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        ctx.error(T)
+    err_us = (time.perf_counter() - t0) * 1e6 / n_calls
+    reg1 = O.Registration(factor=O.FACTOR_ICP, num_threads=0)
+    reg1.linearize(tc, tt, sc, T)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        reg1.linearize(tc, tt, sc, T)
+    cpu_lin_us = (time.perf_counter() - t0) * 1e6 / 20
+    ctx.close()
+    return {
+        "what": "BASELINE configs[0]: bundled target.ply <-> source.ply, point-to-point ICP, helper align() (0.25 m voxel grid, k=10 features, kd-tree, LM <= 20 iterations); GPU: C++ host mirror + device pipeline, wall clock per align() incl. both uploads; CPU: oracle restatement, 1 thread",
+        "points": {"target_raw": len(tgt), "source_raw": len(src), "target": r.target_size, "source": r.source_size},
+        "helper_align_ms": gpu_ms,
+        "cpu_1thread_ms": {"preprocess": cpu_pre_ms, "align": (t2 - t1) * 1e3, "total": cpu_total_ms},
+        "iterations": {"gpu": r.iterations, "cpu": int(ref.iterations)},
+        "pose_vs_cpu": {"rot_rad": rot, "trans_m": trans},
+        "pose_vs_T_target_source_txt": {"rot_rad": rot_f, "trans_m": trans_f},
+        "sgb_linearize_call_us": lin_us,
+        "sgb_error_call_us": err_us,
+        "cpu_1thread_linearize_us": cpu_lin_us,
+    }
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -1001,6 +1070,11 @@ def run_ours(args):
         barrier()
         if fused:
             ctx.comm_disconnect()
+        if world == 1:
+            try:
+                extras["c1"] = run_c1(B)
+            except Exception as e:
+                extras["c1"] = {"error": repr(e)}
         if world == 1 and args.c3_frames > 1:
             try:
                 extras["c3"] = run_c3(B, args.c3_frames)
