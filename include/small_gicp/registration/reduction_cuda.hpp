@@ -91,10 +91,11 @@ struct MirrorKey {
 
 struct DeviceMirror {
   sgb_ctx* ctx = nullptr;
+  bool owned = true;  // false: borrowed through use_context(), not destroyed here
   MirrorKey target, tree, source;
   bool target_valid = false, source_valid = false;
   ~DeviceMirror() {
-    if (ctx) sgb_destroy(ctx);
+    if (ctx && owned) sgb_destroy(ctx);
   }
 };
 
@@ -221,6 +222,14 @@ struct ParallelReductionCUDA {
   /// with a long-lived factor vector).
   void invalidate() const {
     if (mirror_) mirror_->target_valid = mirror_->source_valid = false;
+  }
+
+  /// Run on a context the caller owns (and keeps alive) instead of creating one: creating a context costs milliseconds (stream, page-locked
+  /// result slot, first allocations) -- code that constructs a Registration<> per align() call shares one long-lived context this way.
+  void use_context(sgb_ctx* ctx) const {
+    mirror_ = std::make_shared<cuda_detail::DeviceMirror>();
+    mirror_->ctx = ctx;
+    mirror_->owned = false;
   }
 
   sgb_ctx* context() const {

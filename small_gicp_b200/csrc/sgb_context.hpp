@@ -94,6 +94,7 @@ struct sgb_ctx {
   uint32_t class_fallback_pct = 85;  // more than this share of the chunks listed (pending lanes almost everywhere): curve order instead of the lists
   float class_wide_cells = 2.0f;     // search radius (in cells) from which a chunk counts as wide
   bool grid_curve_order = true;  // block lists laid out along a Morton curve (profiling switch SGB_GRID_ORDER=0: raster order of the packed coordinates)
+  bool use_ring_scan = false;    // profiling switch SGB_RING_SCAN=1: many pending queries through a thread-per-query ring scan (measured: much slower)
   bool tma_leaf = false;         // profiling switch SGB_TMA_LEAF=1 (A/B of the north-star's TMA leaf staging)
   bool use_chunk_classes = true; // profiling switch SGB_CHUNK_CLASSES=0: the packet search scans all chunks in curve order
   int packet_parity = 0;

@@ -579,6 +579,88 @@ __global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_
   }
 }
 
+#ifdef SGB_PROFILING
+// ---------------------------------------------------------------------------------------------------------------
+// Many pending queries AND a rejector whose radius the ring covers (DistanceRejector(1 m) with the usual cell: 2.5 c = 1.1 m): one THREAD
+// per pending query finishes it exactly from the block lists alone -- the 26 blocks at stride 2 around its own one (which the probe has
+// already scanned), each skipped when its box lies beyond the best distance so far.  Everything within sqrt(max_dist_sq) of the query is
+// inside those 27 blocks, so whatever is nearest there is the exact nearest neighbour, or provably nothing is in range.  The idea: trade
+// the packet walk's ~3,350 warp instructions per 32-query chunk for per-thread scans as wide as each query's own search ball.
+// MEASURED AND REJECTED (r02m, SGB_RING_SCAN=1): 0.417 vs 0.241 ms at the identity pose, 0.275 vs 0.181 ms at T1 -- up to 26 dependent
+// lookup + scan round trips per thread with neighbouring lanes needing different blocks is far slower than one shared, divergence-free
+// walk.  Exact (test_search_structures_agree: device-kd/grid-ring-scan-pending); profiling library only.
+// ---------------------------------------------------------------------------------------------------------------
+// the 26 neighbours of the centre block, faces first, then edges, then corners; ox | oy << 2 | oz << 4 with o in {0, 1, 2} = {-1, 0, +1}
+__constant__ unsigned char kRingOrder[26] = {
+  0x14, 0x16, 0x11, 0x19, 0x05, 0x25,                                                  // faces:  x-, x+, y-, y+, z-, z+
+  0x10, 0x12, 0x18, 0x1a, 0x04, 0x06, 0x24, 0x26, 0x01, 0x09, 0x21, 0x29,            // edges:  xy (4), xz (4), yz (4)
+  0x00, 0x02, 0x08, 0x0a, 0x20, 0x22, 0x28, 0x2a};                                    // corners
+__global__ void __launch_bounds__(256, 4) ring_scan_kernel(const __grid_constant__ LinParams P, const uint32_t* __restrict__ pending_count,
+                                                           const uint32_t* __restrict__ pending_list, uint32_t min_pending, const float4* __restrict__ grid_pts,
+                                                           const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell) {
+  grid_dependency_wait();  // probe (and the warp-per-query kernel, which exits at once in this regime) wrote corr[] and the pending list
+  const uint32_t count = *pending_count;
+  if (count <= min_pending) return;
+  const double* R = P.T;
+  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
+  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
+  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
+  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
+  const float cell_sq = cell * cell;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const uint32_t i = pending_list[k];
+    const float4 s = __ldg(&P.src.pts[i]);
+    const double sx = s.x, sy = s.y, sz = s.z;
+    const float qx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
+    const float qy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
+    const float qz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
+    float best_d = P.max_dist_sq;
+    uint32_t best = P.corr[i];  // the probe's candidate (own block, or the previous correspondence): an upper bound
+    if (best != kNone) {
+      const float4 t = __ldg(&P.tgt.pts[best]);
+      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < best_d) best_d = d;
+      else best = kNone;  // beyond the rejector's bound: no use
+    }
+    const float ux = (qx - g.origin[0]) * g.inv_cell, uy = (qy - g.origin[1]) * g.inv_cell, uz = (qz - g.origin[2]) * g.inv_cell;
+    const int ax = static_cast<int>(fminf(fmaxf(floorf(ux - 0.5f), -1e5f), 1e5f)), ay = static_cast<int>(fminf(fmaxf(floorf(uy - 0.5f), -1e5f), 1e5f)),
+              az = static_cast<int>(fminf(fmaxf(floorf(uz - 0.5f), -1e5f), 1e5f));
+    // per axis: squared distance (cell units, less the rounding slack) from the query to the lower / own / upper block slab
+    // (the query sits inside its own slab, so that distance is zero; scalars, not arrays: dynamic indexing would go to local memory)
+    auto slab = [&](float u, int a, int o) {
+      const float l = static_cast<float>(a + 2 * (o - 1));
+      const float f = fmaxf(fmaxf(l - u, u - (l + 2.0f)) - kGridSlack, 0.0f);
+      return f * f * cell_sq;
+    };
+    const float ex0 = slab(ux, ax, 0), ex2 = slab(ux, ax, 2), ey0 = slab(uy, ay, 0), ey2 = slab(uy, ay, 2), ez0 = slab(uz, az, 0), ez2 = slab(uz, az, 2);
+    // nearer blocks first: faces, then edges, then corners of the 3 x 3 x 3 arrangement (the centre is the probe's own block)
+    {
+#pragma unroll 1
+      for (int b = 0; b < 26; b++) {
+        const int code = kRingOrder[b], ox = code & 3, oy = (code >> 2) & 3, oz = code >> 4;
+        const float bd = (ox == 0 ? ex0 : (ox == 2 ? ex2 : 0.0f)) + (oy == 0 ? ey0 : (oy == 2 ? ey2 : 0.0f)) + (oz == 0 ? ez0 : (oz == 2 ? ez2 : 0.0f));
+        if (!(bd < best_d)) continue;
+        const uint2 e = grid_lookup(table, mask, ax + 2 * (ox - 1), ay + 2 * (oy - 1), az + 2 * (oz - 1));
+        const float4* __restrict__ cp = grid_pts + e.x;
+#pragma unroll 4
+        for (uint32_t j = 0; j < e.y; j++) {
+          const float4 t = __ldg(&cp[j]);
+          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d) {
+            best_d = d;
+            best = __float_as_uint(t.w);
+          }
+        }
+      }
+    }
+    P.corr[i] = best;
+  }
+}
+
+#endif  // SGB_PROFILING
+
 // per-leaf spacing estimate from the packet records (two largest box extents / count) for the choice of the cell size
 __global__ void grid_spacing_kernel(const float4* __restrict__ pnodes, uint32_t n_inner, float* out) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -657,6 +739,15 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
 #endif
   grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
   return cudaGetLastError();
+}
+
+cudaError_t launch_ring_scan(const LinParams& P, const uint32_t* pending_count, const uint32_t* pending_list, uint32_t min_pending, const float4* grid_pts,
+                             const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid, cudaStream_t st) {
+#ifndef SGB_PROFILING
+  return cudaErrorNotSupported;
+#else
+  return launch_dependent(ring_scan_kernel, grid, 256, 0, st, P, pending_count, pending_list, min_pending, grid_pts, block_table, capacity - 1u, g, 1.0f / g.inv_cell);
+#endif
 }
 
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,

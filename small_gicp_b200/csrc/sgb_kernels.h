@@ -103,6 +103,14 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
 cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
                                   uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
                                   cudaStream_t st);
+/// thread-per-query ring scan (many pending queries, rejector radius within the ring's reach); grid-stride
+cudaError_t launch_ring_scan(const LinParams& P, const uint32_t* pending_count, const uint32_t* pending_list, uint32_t min_pending, const float4* grid_pts,
+                             const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid, cudaStream_t st);
+/// what the 27-block ring is guaranteed to cover: squared radius ((2.5 - slack) cells)^2
+inline float ring_cover_sq(float cell) {
+  const float c = (2.5f - 4e-3f) * cell;
+  return c * c;
+}
 // device-side tree construction (sgb_kernels.cu)
 constexpr uint32_t kLbvhLeafPoints = 32;
 cudaError_t launch_curve_keys(const float4* pts, size_t n, const double* centre4, uint64_t* keys, uint32_t* vals, int sm_count, cudaStream_t st);

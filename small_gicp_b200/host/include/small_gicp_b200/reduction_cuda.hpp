@@ -76,10 +76,11 @@ struct CloudArrays {
 
 struct DeviceMirror {
   sgb_ctx* ctx = nullptr;
+  bool owned = true;  // false: borrowed through use_context(), not destroyed here
   MirrorKey target_key, tree_key, source_key;
   bool target_valid = false, source_valid = false;
   ~DeviceMirror() {
-    if (ctx) sgb_destroy(ctx);
+    if (ctx && owned) sgb_destroy(ctx);
   }
 };
 
@@ -150,6 +151,15 @@ struct ParallelReductionCUDA {
   /// Forget the device copies (call after mutating a cloud in place between align() calls).
   void invalidate() const {
     if (mirror) mirror->target_valid = mirror->source_valid = false;
+  }
+
+  /// Run on a context the caller owns (and keeps alive) instead of creating one: creating a context costs milliseconds (stream, page-locked
+  /// result slot, first allocations) -- callers that build a Registration<> per align(), like the helper align() overloads, share one
+  /// long-lived context this way.  Its mirrors are invalidated.
+  void use_context(sgb_ctx* ctx) const {
+    mirror = std::make_shared<detail::DeviceMirror>();
+    mirror->ctx = ctx;
+    mirror->owned = false;
   }
 
   sgb_ctx* context() const {

@@ -113,6 +113,7 @@ inline RegistrationResult align(const PointCloud& target, const PointCloud& sour
                                 const Isometry3d& init_T = Isometry3d::Identity(), const RegistrationSetting& setting = RegistrationSetting()) {
   auto run = [&](auto registration) {
     registration.reduction.device = setting.device;
+    registration.reduction.use_context(detail::helper_context(setting.device));  // one long-lived context per thread, not one per call
     registration.rejector.max_dist_sq = setting.max_correspondence_distance * setting.max_correspondence_distance;
     registration.criteria.rotation_eps = setting.rotation_eps;
     registration.criteria.translation_eps = setting.translation_eps;
@@ -140,6 +141,7 @@ inline RegistrationResult align(const GaussianVoxelMap& target, const PointCloud
   if (setting.type != RegistrationSetting::VGICP) std::cerr << "invalid registration type for GaussianVoxelMap" << std::endl;
   Registration<GICPFactor, ParallelReductionCUDA> registration;
   registration.reduction.device = setting.device;
+  registration.reduction.use_context(detail::helper_context(setting.device));
   registration.criteria.rotation_eps = setting.rotation_eps;
   registration.criteria.translation_eps = setting.translation_eps;
   registration.optimizer.max_iterations = setting.max_iterations;
@@ -171,6 +173,7 @@ inline RegistrationResult align(const PointCloud& target_raw, const PointCloud& 
   const DeviceKdTree<PointCloud> tree(target);
   auto run = [&](auto registration) {
     registration.reduction.device = setting.device;
+    registration.reduction.use_context(detail::helper_context(setting.device));
     registration.rejector.max_dist_sq = setting.max_correspondence_distance * setting.max_correspondence_distance;
     registration.criteria.rotation_eps = setting.rotation_eps;
     registration.criteria.translation_eps = setting.translation_eps;
