@@ -15,7 +15,9 @@
  * stream, so sgb_{target,source}_set_points / sgb_target_set_voxelmap may return before it has been
  * read -- leave such a buffer unchanged until sgb_synchronize() or any call that returns results to
  * the host (sgb_linearize, sgb_error, sgb_correspondences, ...).  Pageable memory (std::vector,
- * numpy) is consumed when the call returns.  Host layouts are exactly the reference's in-memory layouts so that the header
+ * numpy) is consumed when the call returns.  Every bulk input / output pointer (points, normals, covariances, queries, feature and
+ * correspondence outputs) may also be a DEVICE pointer of the context's GPU (copies use cudaMemcpyDefault): a device-resident producer hands
+ * its buffers over without a host round trip.  Host layouts are exactly the reference's in-memory layouts so that the header
  * glue can pass `cloud.points[0].data()` etc. without repacking:
  *   points / normals : N x 4 doubles (x,y,z,1) / (nx,ny,nz,0)   -- std::vector<Eigen::Vector4d>,
  *                      include/small_gicp/points/point_cloud.hpp:69-70

@@ -458,6 +458,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_CHUNK_CLASSES")) ctx->use_chunk_classes = !(s[0] == '0');  // 0 = no work lists by cost class: chunks in curve order
   if (const char* s = getenv("SGB_GRID_ORDER")) ctx->grid_curve_order = !(s[0] == '0');  // 0 = block lists in raster order of the packed block coordinates
   if (const char* s = getenv("SGB_RING_SCAN")) ctx->use_ring_scan = (s[0] == '1');  // 1 = many pending queries through the thread-per-query ring scan (rejected A/B)
+  if (const char* s = getenv("SGB_KD_SMEM")) ctx->kd_smem_refine = !(s[0] == '0');  // 0 = kd refinement with one radix sort per level all the way down
   if (const char* s = getenv("SGB_TMA_LEAF")) ctx->tma_leaf = (s[0] == '1');  // 1 = dense leaf scans read a cp.async.bulk (TMA) staged copy of the leaf
   if (const char* s = getenv("SGB_CLASS_FALLBACK_PCT")) ctx->class_fallback_pct = static_cast<uint32_t>(std::max(0, atoi(s)));
   if (const char* s = getenv("SGB_CLASS_WIDE")) ctx->class_wide_cells = static_cast<float>(atof(s));

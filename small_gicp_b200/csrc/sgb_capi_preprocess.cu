@@ -50,7 +50,9 @@ int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d
     // position boundaries of the next level are then exactly the median splits of a kd-tree (same quality as the host
     // builder, ~d radix sorts instead of a D2H + recursive host build + H2D)
     CU(ctx->pre_boxes.reserve(static_cast<size_t>(P) * 6 * sizeof(uint32_t)));
-    for (int level = 0; level < d; level++) {
+    // top levels (nodes larger than a shared-memory segment): one radix sort per level; every subtree below is refined by ONE launch
+    const int level0 = ctx->kd_smem_refine ? static_cast<int>(kd_smem_first_level(static_cast<uint32_t>(n), static_cast<uint32_t>(d))) : d;
+    for (int level = 0; level < level0; level++) {
       const uint32_t count = 1u << level;
       CU(launch_kd_level_keys(leaf_pts.as<float4>(), static_cast<uint32_t>(n), count, ctx->pre_boxes.as<uint32_t>(), ctx->keys_in.as<uint64_t>(), ctx->stream));
       CU(cudaMemcpyAsync(ctx->vals_in.p, perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -63,6 +65,10 @@ int build_lbvh(sgb_ctx* ctx, const float4* d_orig_pts, size_t n, const double* d
       CU(launch_gather(perm.as<uint32_t>(), n, d_orig_pts, leaf_pts.as<float4>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sm_count,
                        ctx->stream));
       ctx->launches += 8;
+    }
+    if (level0 < d) {
+      CU(launch_kd_refine_smem(leaf_pts.as<float4>(), perm.as<uint32_t>(), static_cast<uint32_t>(n), static_cast<uint32_t>(level0), static_cast<uint32_t>(d), ctx->stream));
+      ctx->launches += 1;
     }
   }
   int launches = 0;

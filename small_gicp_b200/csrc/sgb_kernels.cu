@@ -565,6 +565,86 @@ __global__ void kd_keys_kernel(const float4* __restrict__ pts, uint32_t n, uint3
   keys[i] = (static_cast<uint64_t>(node) << 32) | float_flip(c);
 }
 
+// The same median-split refinement for a whole SUBTREE of at most kKdSegMax points in ONE launch: CTA b owns node b of level `level0`
+// (a contiguous position range), keeps its points in shared memory and runs every remaining level there -- per level: node boxes
+// (shared-memory atomics on order-preserving integer images of the floats), key = (node, coordinate along the node's widest axis),
+// bitonic sort of (key, slot), permutation of the points.  Above level0 a level is ~12 launches (boxes, keys, radix sort, gather); for a
+// 16k-point frame that was 9 levels = ~110 launches = 0.9 ms of launch latency, now 3 levels + this kernel.  Same keys, same balanced
+// position boundaries as the per-level path (ties may land differently -- any order is a valid tree).
+constexpr uint32_t kKdSegMax = 2048;
+constexpr uint32_t kKdSegNodes = 128;
+__global__ void __launch_bounds__(1024) kd_refine_smem_kernel(float4* __restrict__ leaf_pts, uint32_t* __restrict__ perm, uint32_t n, uint32_t level0, uint32_t levels) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float4* s_pts = reinterpret_cast<float4*>(s_raw);                                            // [2][kKdSegMax]
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw + 2 * kKdSegMax * sizeof(float4));  // [kKdSegMax]
+  uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_key + kKdSegMax);                            // [kKdSegMax]
+  uint32_t* s_box = s_idx + kKdSegMax;                                                         // [kKdSegNodes][6]
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t first = tree_bound(b, 1u << level0, n), last = tree_bound(b + 1u, 1u << level0, n), m = last - first;
+  for (uint32_t t = tid; t < m; t += blockDim.x) s_pts[t] = leaf_pts[first + t];
+  uint32_t cur = 0;
+  __syncthreads();
+  for (uint32_t level = level0; level < levels; level++) {
+    const uint32_t count = 1u << level, node_first = b << (level - level0), n_nodes = 1u << (level - level0);
+    for (uint32_t t = tid; t < n_nodes * 6u; t += blockDim.x) s_box[t] = (t % 6u) < 3u ? 0xFFFFFFFFu : 0u;
+    __syncthreads();
+    const float4* P0 = s_pts + cur * kKdSegMax;
+    for (uint32_t t = tid; t < m; t += blockDim.x) {
+      const float4 p = P0[t];
+      uint32_t* bx = s_box + (tree_node_of(first + t, count, n) - node_first) * 6u;
+      atomicMin(&bx[0], float_flip(p.x));
+      atomicMin(&bx[1], float_flip(p.y));
+      atomicMin(&bx[2], float_flip(p.z));
+      atomicMax(&bx[3], float_flip(p.x));
+      atomicMax(&bx[4], float_flip(p.y));
+      atomicMax(&bx[5], float_flip(p.z));
+    }
+    __syncthreads();
+    for (uint32_t t = tid; t < kKdSegMax; t += blockDim.x) {
+      unsigned long long key = ~0ull;  // padding sorts to the end
+      if (t < m) {
+        const uint32_t node = tree_node_of(first + t, count, n) - node_first;
+        const uint32_t* bx = s_box + node * 6u;
+        const float ex = float_unflip(bx[3]) - float_unflip(bx[0]), ey = float_unflip(bx[4]) - float_unflip(bx[1]), ez = float_unflip(bx[5]) - float_unflip(bx[2]);
+        const float4 p = P0[t];
+        const float c = ex >= ey ? (ex >= ez ? p.x : p.z) : (ey >= ez ? p.y : p.z);
+        key = (static_cast<unsigned long long>(node) << 32) | float_flip(c);
+      }
+      s_key[t] = key;
+      s_idx[t] = t;
+    }
+    __syncthreads();
+    // bitonic sort of (key, slot) over kKdSegMax entries: one compare-exchange per thread and step
+    for (uint32_t k = 2; k <= kKdSegMax; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = tid; t < kKdSegMax / 2u; t += blockDim.x) {
+          const uint32_t lo = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), hi = lo | j;
+          const bool up = (lo & k) == 0u;
+          const unsigned long long a = s_key[lo], c = s_key[hi];
+          if ((a > c) == up) {
+            s_key[lo] = c;
+            s_key[hi] = a;
+            const uint32_t ia = s_idx[lo];
+            s_idx[lo] = s_idx[hi];
+            s_idx[hi] = ia;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    float4* P1 = s_pts + (cur ^ 1u) * kKdSegMax;
+    for (uint32_t t = tid; t < m; t += blockDim.x) P1[t] = P0[s_idx[t]];
+    cur ^= 1u;
+    __syncthreads();
+  }
+  const float4* Pf = s_pts + cur * kKdSegMax;
+  for (uint32_t t = tid; t < m; t += blockDim.x) {
+    const float4 p = Pf[t];
+    leaf_pts[first + t] = p;
+    perm[first + t] = static_cast<uint32_t>(__float_as_int(p.w));  // w carries the original index through every permutation
+  }
+}
+
 // one warp per leaf slot: bounding box of its (at most 32) consecutive points -> the parent's child record
 __global__ void lbvh_leaf_kernel(const float4* __restrict__ leaf_pts, uint32_t n, uint32_t P, float4* pnodes) {
   const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
@@ -630,6 +710,25 @@ cudaError_t launch_kd_level_keys(const float4* cur_pts, uint32_t n, uint32_t cou
   kd_boxes_init_kernel<<<(count * 6u + 255u) / 256u, 256, 0, st>>>(boxes, count);
   kd_boxes_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(cur_pts, n, count, boxes);
   kd_keys_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(cur_pts, n, count, boxes, keys);
+  return cudaGetLastError();
+}
+
+/// first level whose nodes hold at most kKdSegMax points (from there on kd_refine_smem_kernel refines whole subtrees in shared memory)
+uint32_t kd_smem_first_level(uint32_t n, uint32_t levels) {
+  uint32_t l = 0;
+  while (l < levels && (static_cast<uint64_t>(n) + (1ull << l) - 1ull) / (1ull << l) > kKdSegMax) l++;
+  return l;
+}
+cudaError_t launch_kd_refine_smem(float4* leaf_pts, uint32_t* perm, uint32_t n, uint32_t level0, uint32_t levels, cudaStream_t st) {
+  if (level0 >= levels) return cudaSuccess;
+  const size_t smem = 2 * kKdSegMax * sizeof(float4) + kKdSegMax * (sizeof(unsigned long long) + sizeof(uint32_t)) + kKdSegNodes * 6 * sizeof(uint32_t);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kd_refine_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kd_refine_smem_kernel<<<1u << level0, 1024, smem, st>>>(leaf_pts, perm, n, level0, levels);
   return cudaGetLastError();
 }
 

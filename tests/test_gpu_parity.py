@@ -346,7 +346,7 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     sg = _sg()
     results = {}
     switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_PROBE_TAIL", "SGB_TMA_LEAF",
-                "SGB_CHUNK_CLASSES", "SGB_CLASS_FALLBACK_PCT", "SGB_RING_SCAN")
+                "SGB_CHUNK_CLASSES", "SGB_CLASS_FALLBACK_PCT", "SGB_RING_SCAN", "SGB_KD_SMEM")
     for name, env, own in (
         ("device-kd/grid", {}, True),
         ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
@@ -368,6 +368,8 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
         ("device-kd/packet-class-lists-never", {"SGB_PENDING_DIV": "1000000", "SGB_CLASS_FALLBACK_PCT": "0"}, True),
         ("device-kd/grid-small-cells-ring-scan", {"SGB_GRID_CELL": "1.2", "SGB_PENDING_DIV": "1000000", "SGB_RING_SCAN": "1"}, True),
         ("device-lbvh/grid", {"SGB_TREE": "lbvh"}, True),
+        ("device-kd-radix-levels/grid", {"SGB_KD_SMEM": "0"}, True),  # kd refinement with one radix sort per level all the way down
+        ("device-kd-radix-levels/no-grid", {"SGB_KD_SMEM": "0", "SGB_GRID": "0"}, True),
         ("host-kd/packet", {"SGB_TREE": "host"}, True),
         ("reference-kd/packet", {}, False),
         ("reference-kd/per-thread", {"SGB_SEARCH": "1"}, False),
