@@ -1126,7 +1126,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm",
-                "kernel": "one sgb_linearize = sgb::grid_probe_blocks_kernel + pending_search_kernel | packet_search_kernel (picked on the device) + factor_reduce_kernel<2,0>: four launches, timed together",
+                "kernel": "one sgb_linearize = sgb::grid_probe_blocks_kernel + packet_search_kernel (few pending queries: warp-per-query ring search, many: packet walk; picked on the device) + factor_reduce_kernel<2,0>: three launches, timed together",
                 "achieved": achieved,
                 "peak": peak,
                 "peak_source": peak_src,

@@ -1,17 +1,17 @@
 #!/bin/bash
-# ncu evidence for the four launches of sgb_linearize over one pass of the bench's pose schedule (T0 .. T4).
-# Launch numbering (kernels matching the filter): rank 0's trajectory 5 x 4 = 20, the all-rank trajectory 5 x 4 = 20, warm-up 5 x 4 = 20,
-# then the load roll: with SGB_BENCH_ROLL=5 its 20 launches are exactly one pass over the 5 poses -> -s 60 -c 20.
+# ncu evidence for the three launches of sgb_linearize over one pass of the bench's pose schedule (T0 .. T4).
+# Launch numbering (kernels matching the filter): rank 0's trajectory 5 x 3 = 15, the all-rank trajectory 5 x 3 = 15, warm-up 5 x 3 = 15,
+# then the load roll: with SGB_BENCH_ROLL=5 its 15 launches are exactly one pass over the 5 poses -> -s 45 -c 15.
 TAG=${1:-r02n}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-KERNELS='regex:grid_probe|pending_search|packet_search|factor_reduce'
+KERNELS='regex:grid_probe|packet_search|factor_reduce'
 # (1) launch list of the timed region: device time of every launch (cold-cache, serialised: shares, not absolutes)
-SGB_BENCH_ROLL=5 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 60 -c 40 --csv --log-file $OUT/launches_timed.csv \
+SGB_BENCH_ROLL=5 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 45 -c 30 --csv --log-file $OUT/launches_timed.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > $OUT/ncu_launches.log 2>&1
 echo "launch list rc=$?"; wc -l $OUT/launches_timed.csv
 # (2) full capture of one pass over the poses
-SGB_BENCH_ROLL=5 timeout 600 ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 60 -c 20 -f -o $OUT/prof_linearize \
+SGB_BENCH_ROLL=5 timeout 600 ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 45 -c 15 -f -o $OUT/prof_linearize \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > $OUT/ncu_full.log 2>&1
 echo "full rc=$?"; tail -3 $OUT/ncu_full.log; ls -la $OUT
 # (3) the bench line of the same build, for the record

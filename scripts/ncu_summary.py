@@ -41,9 +41,10 @@ def main():
             )
         )
     assert rows[1][hdr.index("dram__bytes_read.sum")] == "Mbyte" and rows[1][hdr.index("gpu__time_duration.sum")] == "us"
-    groups = [recs[k : k + 4] for k in range(0, len(recs) - len(recs) % 4, 4)]
-    conv = [x for x in groups if x[2]["dur"] < 20.0]  # packet search exits at once: few queries pending
-    mis = [x for x in groups if x[2]["dur"] >= 20.0]
+    K = 3  # launches per linearize: probe, packet_search (few pending: warp-per-query ring search; many: packet walk), factor_reduce
+    groups = [recs[k : k + K] for k in range(0, len(recs) - len(recs) % K, K)]
+    conv = [x for x in groups if x[1]["dur"] < 40.0]  # few queries pending: the finishing kernel runs its warp-per-query regime
+    mis = [x for x in groups if x[1]["dur"] >= 40.0]
 
     def avg(gs, i, key):
         return sum(x[i][key] for x in gs) / len(gs)
@@ -51,13 +52,13 @@ def main():
     b = json.load(open(os.path.join(src, "bench.json")))
     r = json.load(open(os.path.join(src, "bench_ref.json")))
     L = []
-    L.append(f"# {os.path.basename(dst)}/{tag} -- the four launches of `sgb_linearize` (1M x 1M synthetic GICP), ncu --set full\n")
-    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|pending_search|packet_search|factor_reduce" -s 60 -c 20 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras` with `SGB_BENCH_ROLL=5` (`scripts/gpu_ncu.sh`)')
+    L.append(f"# {os.path.basename(dst)}/{tag} -- the three launches of `sgb_linearize` (1M x 1M synthetic GICP), ncu --set full\n")
+    L.append('Command: `ncu --set full --clock-control none --import-source on -k regex:"grid_probe|packet_search|factor_reduce" -s 45 -c 15 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras` with `SGB_BENCH_ROLL=5` (`scripts/gpu_ncu.sh`)')
     L.append(f"(k=20 covariances, L2 flushed between steps; the captured launches are one pass over the {len(groups)} poses of the Gauss-Newton trajectory: {len(conv)} converged, {len(mis)} misaligned).")
-    L.append("Which search kernel does the work is decided on the device from the probe's pending counter; the other one exits at once.\n")
+    L.append("Which regime of the finishing search kernel runs is decided on the device from the probe's pending counter.\n")
     L.append(f"## Converged poses -- mean of {len(conv)} linearizes\n")
-    L.append("| metric | grid_probe_blocks | pending_search (ring) | packet_search (exits) | factor_reduce<GICP,none> |")
-    L.append("|---|---|---|---|---|")
+    L.append("| metric | grid_probe_blocks | packet_search (warp-per-query regime) | factor_reduce<GICP,none> |")
+    L.append("|---|---|---|---|")
     for label, key, fmt in (
         ("gpu__time_duration (under ncu, us)", "dur", "{:.1f}"),
         ("dram read + write (MB)", "mb", "{:.1f}"),
@@ -66,17 +67,17 @@ def main():
         ("L2 hit (%)", "l2", "{:.0f}"),
         ("FP64 pipe active (%)", "fp64", "{:.1f}"),
     ):
-        L.append(f"| {label} | " + " | ".join(fmt.format(avg(conv, i, key)) for i in range(4)) + " |")
-    L.append("| warp instructions (M) | " + " | ".join(f"{avg(conv, i, 'inst') / 1e6:.2f}" for i in range(4)) + " |")
-    L.append("| threads per instruction | " + " | ".join(conv[0][i]["thr"] for i in range(4)) + " |")
-    L.append("| registers, grid | " + " | ".join(f"{conv[0][i]['regs']}, {conv[0][i]['grid']}" for i in range(4)) + " |")
-    L.append(f"\nSum: **{sum(avg(conv, i, 'dur') for i in range(4)):.0f} us**, {sum(avg(conv, i, 'mb') for i in range(4)):.0f} MB of DRAM traffic per linearize.\n")
+        L.append(f"| {label} | " + " | ".join(fmt.format(avg(conv, i, key)) for i in range(K)) + " |")
+    L.append("| warp instructions (M) | " + " | ".join(f"{avg(conv, i, 'inst') / 1e6:.2f}" for i in range(K)) + " |")
+    L.append("| threads per instruction | " + " | ".join(conv[0][i]["thr"] for i in range(K)) + " |")
+    L.append("| registers, grid | " + " | ".join(f"{conv[0][i]['regs']}, {conv[0][i]['grid']}" for i in range(K)) + " |")
+    L.append(f"\nSum: **{sum(avg(conv, i, 'dur') for i in range(K)):.0f} us**, {sum(avg(conv, i, 'mb') for i in range(K)):.0f} MB of DRAM traffic per linearize.\n")
     if mis:
-        L.append("## Misaligned first iterations -- more than N/16 queries pending: the packet search takes them\n")
-        L.append("| pose | probe us | pending us | packet us | factor us | sum us | DRAM MB |")
-        L.append("|---|---|---|---|---|---|---|")
+        L.append("## Misaligned first iterations -- more than N/16 queries pending: the packet walk takes them\n")
+        L.append("| pose | probe us | packet us | factor us | sum us | DRAM MB |")
+        L.append("|---|---|---|---|---|---|")
         for n, x in enumerate(mis):
-            L.append(f"| T{n} | {x[0]['dur']:.1f} | {x[1]['dur']:.1f} | {x[2]['dur']:.1f} | {x[3]['dur']:.1f} | {sum(y['dur'] for y in x):.0f} | {sum(y['mb'] for y in x):.0f} |")
+            L.append(f"| T{n} | {x[0]['dur']:.1f} | {x[1]['dur']:.1f} | {x[2]['dur']:.1f} | {sum(y['dur'] for y in x):.0f} | {sum(y['mb'] for y in x):.0f} |")
     traffic = sum(sum(y["mb"] for y in x) for x in groups) / len(groups)
     kernel_us = sum(sum(y["dur"] for y in x) for x in groups) / len(groups)
     L.append(f"\nMean over the poses: {kernel_us:.0f} us of kernel time (cold, serialised by the profiler), **{traffic:.1f} MB** of DRAM traffic per linearize")
@@ -93,7 +94,7 @@ def main():
     json.dump(
         {
             "dram_bytes_per_launch": traffic * 1e6,
-            "source": f"{dst}/{tag}_linearize.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the four launches of one sgb_linearize, mean over the poses of the bench trajectory, 1M x 1M GICP)",
+            "source": f"{dst}/{tag}_linearize.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the three launches of one sgb_linearize, mean over the poses of the bench trajectory, 1M x 1M GICP)",
         },
         open(os.path.join(os.path.dirname(dst.rstrip("/")), "linearize_traffic.json"), "w"),
         indent=1,

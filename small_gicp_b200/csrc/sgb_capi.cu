@@ -198,6 +198,7 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
       const uint8_t* settled = nullptr;
       const uint32_t* pending_count = nullptr;
       ChunkClasses cc = {};
+      PendingParams pp = {};
       // more pending queries than this: packet search over the chunk-ordered queries, else a warp per pending query
       const uint32_t pending_split = static_cast<uint32_t>(ctx->n_src / static_cast<size_t>(ctx->pending_div));
       if (ctx->grid_ready) {
@@ -236,13 +237,18 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
           cc.mid_r2 = cell * cell;
           cc.fallback_pct = ctx->class_fallback_pct;
         }
+        CU(ctx->grid_pending_q.reserve(ctx->n_src * sizeof(float4)));
         CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->probe_batch_tail, ctx->grid_state.as<uint8_t>(), pc,
-                             plist, pbase + (ctx->pending_parity ^ 1), cc, ctx->stream));
+                             plist, ctx->grid_pending_q.as<float4>(), pbase + (ctx->pending_parity ^ 1), cc, ctx->stream));
         ctx->pending_parity ^= 1;
-        CU(launch_pending_search(P, ctx->tgt_pnodes.as<float4>(), depth, pc, plist, pending_split, ctx->grid_pts.as<float4>(),
-                                 (ctx->grid_blocks && ctx->use_ring) ? ctx->grid_table.as<GridSlot>() : nullptr, ctx->grid_capacity, g, ctx->sm_count * 8,
-                                 ctx->stream));
-        ctx->launches += 2;
+        // the finishing kernel (below) serves both regimes: few pending queries warp-per-query, many through the packet walk
+        pp.list = plist;
+        pp.q = ctx->grid_pending_q.as<float4>();
+        pp.grid_pts = ctx->grid_pts.as<float4>();
+        pp.table = (ctx->grid_blocks && ctx->use_ring) ? ctx->grid_table.as<GridSlot>() : nullptr;
+        pp.capacity = ctx->grid_capacity;
+        pp.g = g;
+        ctx->launches += 1;
         settled = ctx->grid_state.as<uint8_t>();
         pending_count = pc;
       }
@@ -251,12 +257,10 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
       const bool ring_scan = ctx->use_ring_scan && ctx->grid_ready && ctx->grid_blocks && ctx->use_ring && bound <= ring_cover_sq(ctx->grid_cell);
       if (ring_scan) {
         const int rgrid = static_cast<int>(std::min<size_t>((ctx->n_src + 255) / 256, static_cast<size_t>(ctx->sm_count) * 8));
-        GridParams g;
-        for (int a = 0; a < 3; a++) g.origin[a] = ctx->grid_origin[a];
-        g.inv_cell = ctx->grid_inv_cell;
-        g.settle_d2 = ctx->grid_settle_d2;
+        pp.few_only = true;  // the finishing kernel still serves the few-pending regime
         CU(launch_ring_scan(P, pending_count, ctx->grid_pending.as<uint32_t>() + 2, pending_split, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(),
-                            ctx->grid_capacity, g, rgrid, ctx->stream));
+                            ctx->grid_capacity, pp.g, rgrid, ctx->stream));
+        CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, nullptr, nullptr, ChunkClasses{}, pp, false, ctx->stream));
       } else {
       uint32_t *queue = nullptr, *queue_next = nullptr;
       if (ctx->use_packet_queue) {
@@ -268,7 +272,7 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
         queue_next = ctx->packet_queue.as<uint32_t>() + (ctx->packet_parity ^ 1);
         ctx->packet_parity ^= 1;
       }
-      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, cc, ctx->tma_leaf, ctx->stream));
+      CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, queue, queue_next, cc, pp, ctx->tma_leaf, ctx->stream));
       }
 #ifdef SGB_PROFILING
       if (ctx->debug_pending && pending_count) {  // profiling aid: synchronises
@@ -847,6 +851,7 @@ int sgb_source_set_points(sgb_ctx* ctx, size_t n, const double* points, const do
     const void* before = ctx->grid_pending.p;
     CU(ctx->grid_pending.reserve((n + 2) * sizeof(uint32_t)));
     if (ctx->grid_pending.p != before) ctx->pending_clean = false;
+    CU(ctx->grid_pending_q.reserve(n * sizeof(float4)));
   }
   if (int rc = ensure_reduction_buffers(ctx, ctx->sm_count * 8)) return rc;
   {

@@ -81,7 +81,8 @@ struct sgb_ctx {
   size_t n_pnodes = 0;      // packet records of the current target tree
   // uniform-grid front end of the search (sgb_grid.cu)
   bool use_grid = true, grid_ready = false, grid_blocks = true;  // grid_blocks: 2 x 2 x 2 block lists (one lookup per query) instead of per-cell lists
-  sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0] = count, [1..] = pending query positions
+  sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0], [1] = alternating counters, [2..] = pending query positions
+  sgb::DevBuf grid_pending_q;  // parallel to the list: transformed query + squared distance of the probe's best candidate
   bool grid_blocks_wanted = true, use_ring = true, debug_pending = false;  // profiling switches (sgb_create)
   int pending_div = 16;           // more than n_src / pending_div pending queries: packet search, else a warp per pending query
   double grid_cell_factor = 2.5;  // cell edge in units of the median point spacing (sweep in profiles/r01: 2 / 2.5 / 3 / 4)

@@ -22,28 +22,10 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sgb_device.cuh"
+#include "sgb_grid.cuh"
 #include "sgb_kernels.h"
 
 namespace sgb {
-
-// slack (in cells) for the FP32 cell-coordinate arithmetic: cell indices stay below 2^13 (build_grid), so a coordinate
-// in cell units carries < 1e-3 of rounding error
-constexpr float kGridSlack = 4e-3f;
-
-__device__ __forceinline__ uint64_t grid_key(int ix, int iy, int iz) {
-  return (static_cast<uint64_t>(static_cast<uint32_t>(ix + (1 << 20)) & 0x1fffffu)) | (static_cast<uint64_t>(static_cast<uint32_t>(iy + (1 << 20)) & 0x1fffffu) << 21) |
-         (static_cast<uint64_t>(static_cast<uint32_t>(iz + (1 << 20)) & 0x1fffffu) << 42);
-}
-__device__ __forceinline__ uint32_t grid_hash(int ix, int iy, int iz) {
-  uint32_t h = static_cast<uint32_t>(ix) * 73856093u ^ static_cast<uint32_t>(iy) * 19349663u ^ static_cast<uint32_t>(iz) * 83492791u;
-  h ^= h >> 15;
-  return h;
-}
-__device__ __forceinline__ uint32_t grid_hash_of_key(uint64_t k) {
-  const int ix = static_cast<int>(k & 0x1fffffu) - (1 << 20), iy = static_cast<int>((k >> 21) & 0x1fffffu) - (1 << 20),
-            iz = static_cast<int>((k >> 42) & 0x1fffffu) - (1 << 20);
-  return grid_hash(ix, iy, iz);
-}
 
 // Morton (Z-order) code of the three 21-bit offset coordinates: the ORDER in which the lists are laid out in memory.  The table is keyed
 // by the plain packed coordinates (grid_key); only the sort uses the curve, so that the lists a warp of Hilbert-ordered queries needs --
@@ -135,18 +117,6 @@ __global__ void grid_table_init_kernel(GridSlot* table, uint32_t capacity) {
   }
 }
 
-__device__ __forceinline__ uint2 grid_lookup(const GridSlot* __restrict__ table, uint32_t mask, int ix, int iy, int iz) {
-  const uint64_t k = grid_key(ix, iy, iz);
-  uint32_t slot = grid_hash(ix, iy, iz) & mask;
-  for (;;) {
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&table[slot]));
-    const uint64_t ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
-    if (ek == k) return make_uint2(e.z, e.w);
-    if (ek == ~0ull) return make_uint2(0u, 0u);
-    slot = (slot + 1u) & mask;
-  }
-}
-
 __device__ __forceinline__ void grid_scan(const float4* __restrict__ cp, uint32_t cnt, float fx, float fy, float fz, float& best_d, uint32_t& best) {
 #pragma unroll 4
   for (uint32_t j = 0; j < cnt; j++) {
@@ -168,7 +138,7 @@ __device__ __forceinline__ void grid_scan(const float4* __restrict__ cp, uint32_
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
                                                            const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell_sq, uint8_t* state,
-                                                           uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count) {
+                                                           uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = gi < P.src.n;
   if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
@@ -245,7 +215,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
     uint32_t base = 0;
     if (lane == static_cast<uint32_t>(__ffs(m) - 1)) base = atomicAdd(pending_count, static_cast<uint32_t>(__popc(m)));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (pend) pending_list[base + __popc(m & ((1u << lane) - 1u))] = i;
+    if (pend) {
+      const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+      pending_list[slot] = i;
+      pending_q[slot] = make_float4(fx, fy, fz, (best == kNone || !(best_d < P.max_dist_sq)) ? P.max_dist_sq : best_d);
+    }
   }
 }
 
@@ -261,7 +235,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 template <int MIN_CTAS, bool BATCH_TAIL>
 __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
-                                                               uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, ChunkClasses cc) {
+                                                               uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count,
+                                                               ChunkClasses cc) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = gi < P.src.n;
   if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
@@ -385,197 +360,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
     }
   }
   __syncthreads();
-  if (pend) pending_list[s_base[wib] + __popc(m & ((1u << lane) - 1u))] = i;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Few pending queries (holes, outliers, borders: a few per mille to a few per cent, scattered): one WARP per query.
-// Ring phase first (block lists): 27 lookups in parallel, the lists scanned as one flattened run over all lanes, a
-// hardware min -- a handful of memory round trips.  Only if the ring's radius (2.5 cells) does not decide the query does
-// the warp walk the packet records: every step of a single walk is a dependent load, so a thread per query would be
-// pure latency (measured: 300 us for 1000 queries); with a warp per query a leaf's points are fetched by one coalesced
-// load and reduced by a hardware min, and thousands of walks are in flight at once.  Skipped -- the packet search handles
-// the chunk-ordered queries instead -- when more than `max_pending` queries are pending.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kPendWarps = kLinBlock / 32;
-constexpr int kPendStack = 40;
-
-__device__ __forceinline__ float grid_box_dist2(float qx, float qy, float qz, const float4& lo, const float4& hi) {
-  const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
-  const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
-  const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
-  return dx * dx + dy * dy + dz * dz;
-}
-
-__global__ void __launch_bounds__(kLinBlock) pending_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes,
-                                                                   const uint32_t* __restrict__ pending_count, const uint32_t* __restrict__ pending_list,
-                                                                   uint32_t max_pending, const float4* __restrict__ grid_pts,
-                                                                   const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell) {
-  __shared__ uint2 s_desc[kPendWarps][kPendStack];
-  __shared__ float s_dist[kPendWarps][kPendStack];
-  grid_dependency_wait();  // the probe filled the pending list
-  const uint32_t count = *pending_count;
-  if (count > max_pending) return;
-  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  uint2* desc = s_desc[wib];
-  float* dist = s_dist[wib];
-  const double* R = P.T;
-  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
-  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
-  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
-  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
-  const float4* __restrict__ pts = P.tgt.pts;
-  for (uint32_t k = warp; k < count; k += n_warps) {
-    // everything below is warp-uniform except the leaf scan
-    const uint32_t i = pending_list[k];
-    const float4 s = __ldg(&P.src.pts[i]);
-    const double sx = s.x, sy = s.y, sz = s.z;
-    const float qx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
-    const float qy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
-    const float qz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
-    float best_d = P.max_dist_sq;
-    uint32_t best = kNone;
-    const uint32_t seed = P.corr[i];
-    if (seed != kNone) {
-      const float4 t = __ldg(&pts[seed]);
-      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-      const float d = dx * dx + dy * dy + dz * dz;
-      if (d < best_d) {
-        best_d = d;
-        best = seed;
-      }
-    }
-    if (table) {
-      // Ring phase (block lists): the 3 x 3 x 3 blocks at stride 2 around the query's own block tile the cells
-      // [a - 2, a + 4)^3, i.e. they hold every target point within 2.5 cells of q.  One lookup and one list scan per lane,
-      // all 27 in parallel, then a warp min: a handful of memory round trips instead of the ~45 of a tree walk.
-      const float ux = (qx - g.origin[0]) * g.inv_cell, uy = (qy - g.origin[1]) * g.inv_cell, uz = (qz - g.origin[2]) * g.inv_cell;
-      const int ax = static_cast<int>(fminf(fmaxf(floorf(ux - 0.5f), -1e5f), 1e5f)), ay = static_cast<int>(fminf(fmaxf(floorf(uy - 0.5f), -1e5f), 1e5f)),
-                az = static_cast<int>(fminf(fmaxf(floorf(uz - 0.5f), -1e5f), 1e5f));
-      uint2 e = make_uint2(0u, 0u);
-      if (lane < 27u) {
-        const int bx = ax + 2 * (static_cast<int>(lane % 3u) - 1), by = ay + 2 * (static_cast<int>((lane / 3u) % 3u) - 1),
-                  bz = az + 2 * (static_cast<int>(lane / 9u) - 1);
-        const float ex = fmaxf(fmaxf(static_cast<float>(bx) - ux, ux - static_cast<float>(bx + 2)) - kGridSlack, 0.0f);
-        const float ey = fmaxf(fmaxf(static_cast<float>(by) - uy, uy - static_cast<float>(by + 2)) - kGridSlack, 0.0f);
-        const float ez = fmaxf(fmaxf(static_cast<float>(bz) - uz, uz - static_cast<float>(bz + 2)) - kGridSlack, 0.0f);
-        if ((ex * ex + ey * ey + ez * ez) * cell * cell < best_d) e = grid_lookup(table, mask, bx, by, bz);
-      }
-      // The (typically ~9 non-empty) lists are scanned as ONE flattened run spread over all 32 lanes: point j of the
-      // concatenation goes to lane j mod 32, which finds its list by a shuffle binary search over the exclusive prefix
-      // sums of the counts.  A lane per list would walk up to ~40 points in dependent batches; this is ~7 loads per lane.
-      uint32_t incl = e.y;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= static_cast<uint32_t>(o)) incl += t;
-      }
-      const uint32_t excl = incl - e.y, total = __shfl_sync(0xffffffffu, incl, 31);
-      float my_d = best_d;
-      uint32_t my_best = kNone;
-#pragma unroll 2
-      for (uint32_t base = 0; base < total; base += 32u) {
-        const uint32_t j = base + lane;
-        uint32_t owner = 0;  // largest lane whose exclusive prefix is <= j (empty lists share their successor's prefix and lose)
-#pragma unroll
-        for (uint32_t step = 16u; step >= 1u; step >>= 1) {
-          const uint32_t cand = owner + step;
-          const uint32_t ex = __shfl_sync(0xffffffffu, excl, cand & 31u);
-          if (cand < 32u && ex <= j) owner = cand;
-        }
-        const uint32_t st = __shfl_sync(0xffffffffu, e.x, owner), ex0 = __shfl_sync(0xffffffffu, excl, owner);
-        if (j < total) {
-          const float4 t = __ldg(&grid_pts[st + (j - ex0)]);
-          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-          const float d = dx * dx + dy * dy + dz * dz;
-          if (d < my_d) {
-            my_d = d;
-            my_best = __float_as_uint(t.w);
-          }
-        }
-      }
-      const uint32_t dbits = my_best != kNone ? __float_as_uint(my_d) : 0x7f800000u;
-      const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
-      if (dmin != 0x7f800000u) {
-        const unsigned who = __ballot_sync(0xffffffffu, dbits == dmin);
-        best = __shfl_sync(0xffffffffu, my_best, __ffs(who) - 1);
-        best_d = __uint_as_float(dmin);
-      }
-      const float cover = (2.5f - kGridSlack) * cell;
-      if (best_d <= cover * cover) {  // everything within sqrt(best_d) of q has been examined: exact (or exactly nothing)
-        if (lane == 0) P.corr[i] = best;
-        continue;
-      }
-    }
-    int sp = 0;
-    uint32_t cur = 0;
-    bool expand = true;
-    uint2 leaf = make_uint2(0u, 0u);
-    for (;;) {
-      if (expand) {
-        const float4 n0 = __ldg(&pnodes[cur * 4 + 0]), n1 = __ldg(&pnodes[cur * 4 + 1]);
-        const float4 n2 = __ldg(&pnodes[cur * 4 + 2]), n3 = __ldg(&pnodes[cur * 4 + 3]);
-        const float dl = grid_box_dist2(qx, qy, qz, n0, n1), dr = grid_box_dist2(qx, qy, qz, n2, n3);
-        const bool left_first = dl <= dr;
-        const float dn = left_first ? dl : dr, df = left_first ? dr : dl;
-        const uint2 cl = make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w)), cr = make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w));
-        const uint2 cn = left_first ? cl : cr, cf = left_first ? cr : cl;
-        if (df < best_d && sp < kPendStack) {
-          if (lane == 0) {
-            desc[sp] = cf;
-            dist[sp] = df;
-          }
-          sp++;
-        }
-        if (!(dn < best_d)) {
-          expand = false;
-          continue;
-        }
-        if (cn.y == 0u) {
-          cur = cn.x;
-          continue;
-        }
-        leaf = cn;
-      } else {
-        bool got = false;
-        __syncwarp();
-        while (sp > 0) {
-          sp--;
-          if (dist[sp] < best_d) {
-            leaf = desc[sp];
-            got = true;
-            break;
-          }
-        }
-        __syncwarp();
-        if (!got) break;
-        if (leaf.y == 0u) {
-          cur = leaf.x;
-          expand = true;
-          continue;
-        }
-      }
-      // leaf: lane j takes point j, the nearest comes out of one hardware min (non-negative floats order like their bits)
-      for (uint32_t base = 0; base < leaf.y; base += 32u) {
-        const uint32_t j = base + lane;
-        uint32_t dbits = 0x7f800000u;
-        if (j < leaf.y) {
-          const float4 t = __ldg(&pts[leaf.x + j]);
-          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-          dbits = __float_as_uint(dx * dx + dy * dy + dz * dz);
-        }
-        const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
-        const float d = __uint_as_float(dmin);
-        if (d < best_d) {
-          const unsigned who = __ballot_sync(0xffffffffu, dbits == dmin);  // lowest lane = first point in scan order
-          best_d = d;
-          best = leaf.x + base + (__ffs(who) - 1);
-        }
-      }
-      expand = false;
-    }
-    if (lane == 0) P.corr[i] = best;
+  if (pend) {  // the pending record: who, where (transformed query) and how far its best candidate is -- the finishing kernel needs nothing else
+    const uint32_t slot = s_base[wib] + __popc(m & ((1u << lane) - 1u));
+    pending_list[slot] = i;
+    pending_q[slot] = make_float4(fx, fy, fz, best_d);
   }
 }
 
@@ -709,27 +497,27 @@ cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_s
 }
 
 cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, uint32_t* next_count, const ChunkClasses& cc,
-                              cudaStream_t st) {
+                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count,
+                              const ChunkClasses& cc, cudaStream_t st) {
   // *pending_count must be zero on entry: the previous probe (or the context) cleared it
   const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
 #ifdef SGB_PROFILING
   if (!blocks) {
-    grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, next_count);
+    grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, pending_q, next_count);
     return cudaGetLastError();
   }
   static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;
   if (batch_tail) {
-    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
+    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
     return cudaGetLastError();
   }
   if (ctas == 6) {
-    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
+    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
     return cudaGetLastError();
   }
   if (ctas == 8) {
-    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
+    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
     return cudaGetLastError();
   }
 #else
@@ -737,7 +525,7 @@ cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const 
   (void)batch_tail;
   (void)cell;
 #endif
-  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, next_count, cc);
+  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
   return cudaGetLastError();
 }
 
@@ -748,15 +536,6 @@ cudaError_t launch_ring_scan(const LinParams& P, const uint32_t* pending_count, 
 #else
   return launch_dependent(ring_scan_kernel, grid, 256, 0, st, P, pending_count, pending_list, min_pending, grid_pts, block_table, capacity - 1u, g, 1.0f / g.inv_cell);
 #endif
-}
-
-cudaError_t launch_pending_search(const LinParams& P, const float4* pnodes, int depth, const uint32_t* pending_count, const uint32_t* pending_list,
-                                  uint32_t max_pending, const float4* grid_pts, const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid,
-                                  cudaStream_t st) {
-  if (depth > kPendStack) return cudaErrorInvalidValue;
-  // block_table: the block-list table (enables the ring phase) or null
-  return launch_dependent(pending_search_kernel, grid, kLinBlock, 0, st, P, pnodes, pending_count, pending_list, max_pending, grid_pts, block_table, capacity - 1u, g,
-                          1.0f / g.inv_cell);
 }
 
 }  // namespace sgb

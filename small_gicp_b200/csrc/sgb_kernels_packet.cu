@@ -12,10 +12,12 @@
 // The tree is the kd-tree (same leaves, same permutation) with each inner node carrying the tight bounding boxes of its two
 // children (64 B, "BVH2" layout):  float4[4] = {L.lo|L.a, L.hi|L.b, R.lo|R.a, R.hi|R.b} where a child is a leaf
 // (a = first point, b = count > 0) or an inner node (a = node index, b = 0).
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
 #include "sgb_device.cuh"
+#include "sgb_grid.cuh"
 #include "sgb_kernels.h"
 
 namespace sgb {
@@ -67,7 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 template <bool TMA_LEAF, int MIN_CTAS>
 __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ pnodes, int max_depth,
                                                                   const uint8_t* __restrict__ settled, const uint32_t* __restrict__ pending_count,
-                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, ChunkClasses cc) {
+                                                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, ChunkClasses cc, RingParams ring) {
   // Work distribution: chunks (32 consecutive queries) differ wildly in cost -- all lanes settled by the grid probe, or 32
   // tree walks through a misaligned wall -- and a static stride left a third of the warps idle for the second half of the
   // kernel (profiles/r01/ai: 39-52 % achieved occupancy of 75 %).  With `queue` the warps take their first chunk by rank and
@@ -75,13 +77,21 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
   // (launches of one context are stream-ordered, the next user is the packet search of the NEXT linearize).
   if (queue_next && blockIdx.x == 0 && threadIdx.x == 0) *queue_next = 0u;
   grid_dependency_wait();  // probe / pending search wrote corr[], the settled flags and the pending counter
-  // with the grid front end this kernel only runs when MANY queries are pending (misaligned first iterations); a handful
-  // of scattered pending queries is served by pending_search_kernel instead
-  if (pending_count && *pending_count <= min_pending) return;
   extern __shared__ float s_dist[];  // [max_depth][kLinBlock] per-lane box distance of each pending subtree
   __shared__ uint2 s_child[kPktWarps][40];  // per-warp: the pending subtrees themselves (warp-uniform)
   __shared__ __align__(128) float4 s_leaf[TMA_LEAF ? kPktWarps : 1][32];  // TMA landing zone of the warp's current leaf
   __shared__ __align__(8) uint64_t s_bar[TMA_LEAF ? kPktWarps : 1];
+  // Two regimes, picked from the probe's counter: FEW pending queries (holes, borders, outliers at an aligned pose) -> a warp per query
+  // (ring phase over the block lists, tree walk only beyond its reach: sgb_grid.cuh); MANY (a misaligned first iteration) -> the packet
+  // walk below.  One launch serves both (round 1: two kernels, one of which exited at once -- 3.5 - 5 us per linearize).
+  if (pending_count) {
+    const uint32_t pc = *pending_count;
+    if (pc <= min_pending) {
+      if (pc) pending_search_body(P, pnodes, pc, ring, s_child[threadIdx.x >> 5], s_dist + (threadIdx.x >> 5) * kPendStack);
+      return;
+    }
+    if (ring.few_only) return;
+  }
   uint32_t tma_phase = 0;
   if (TMA_LEAF) {
     if ((threadIdx.x & 31u) == 0) mbar_init(&s_bar[threadIdx.x >> 5], 1);
@@ -277,34 +287,44 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
 
 int packet_occupancy(int max_depth) {
   int nb = 0;
-  const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
+  const size_t smem = std::max(static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock, static_cast<size_t>(kPktWarps) * kPendStack) * sizeof(float);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, packet_search_kernel<false, kPacketCtas>, kLinBlock, smem) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
-                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, const ChunkClasses& cc, bool tma_leaf, cudaStream_t st) {
+                                 uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, const ChunkClasses& cc, const PendingParams& pp, bool tma_leaf, cudaStream_t st) {
   if (max_depth > 40) return cudaErrorInvalidValue;
-  const size_t smem = static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock * sizeof(float);
+  // per-lane box distances of the packet walk; the warp-per-query regime uses the first kPktWarps x kPendStack floats of it
+  const size_t smem = std::max(static_cast<size_t>(max_depth > 0 ? max_depth : 1) * kLinBlock, static_cast<size_t>(kPktWarps) * kPendStack) * sizeof(float);
+  RingParams ring;
+  ring.list = pp.list;
+  ring.q = pp.q;
+  ring.grid_pts = pp.grid_pts;
+  ring.table = pp.table;
+  ring.mask = pp.capacity ? pp.capacity - 1u : 0u;
+  ring.g = pp.g;
+  ring.cell = pp.g.inv_cell > 0.f ? 1.0f / pp.g.inv_cell : 0.f;
+  ring.few_only = pp.few_only;
 #ifdef SGB_PROFILING
   if (tma_leaf) {  // A/B (SGB_TMA_LEAF=1): leaf blocks staged by cp.async.bulk + mbarrier
     if (!settled) {
-      packet_search_kernel<true, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+      packet_search_kernel<true, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc, ring);
       return cudaGetLastError();
     }
-    return launch_dependent(packet_search_kernel<true, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+    return launch_dependent(packet_search_kernel<true, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc, ring);
   }
 #endif
 #ifdef SGB_PROFILING
   static const bool twelve = std::getenv("SGB_PACKET_CTAS") && std::atoi(std::getenv("SGB_PACKET_CTAS")) == 12;  // A/B: 40 registers, 12 CTAs / SM
-  if (twelve && settled) return launch_dependent(packet_search_kernel<false, 12>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+  if (twelve && settled) return launch_dependent(packet_search_kernel<false, 12>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc, ring);
 #endif
   if (!settled) {  // no grid front end: nothing on the stream this launch could overlap with
-    packet_search_kernel<false, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+    packet_search_kernel<false, kPacketCtas><<<grid, kLinBlock, smem, st>>>(P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc, ring);
     return cudaGetLastError();
   }
   (void)tma_leaf;
-  return launch_dependent(packet_search_kernel<false, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc);
+  return launch_dependent(packet_search_kernel<false, kPacketCtas>, grid, kLinBlock, smem, st, P, pnodes, max_depth, settled, pending_count, min_pending, queue, queue_next, cc, ring);
 }
 
 }  // namespace sgb
