@@ -8,6 +8,7 @@
 // Search and factor phases run back to back on the context's stream; the only extra traffic is the 4-byte correspondence
 // per point that sgb_error()/sgb_correspondences() need anyway.
 #include <cfloat>
+#include <cstdlib>
 
 #include "sgb_device.cuh"
 #include "sgb_kernels.h"
@@ -157,8 +158,10 @@ struct FactorFields {
 };
 constexpr int kFactorStages = 3;
 
-template <int FACTOR, int ROBUST>
-__global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ LinParams P) {
+// NREG: register budget per thread = resident CTAs per SM (128 -> 4 CTAs x 4 warps, no spills; 96 -> 5 CTAs; 80 -> 6, both with spills and slower): the algebra is a chain of
+// dependent FP64 operations and the kernel is short of warps, not of FP64 pipe (41 % active) -- A/B in profiles/r02/b_experiments.md.
+template <int FACTOR, int ROBUST, int NREG>
+__global__ void __maxnreg__(NREG) factor_reduce_kernel(const __grid_constant__ LinParams P) {
   using F = FactorFields<FACTOR>;
   extern __shared__ float4 s_zone[];  // [kFactorStages][F::kAll][kLinBlock]
   __shared__ uint32_t s_corr[kFactorStages][kLinBlock];
@@ -229,10 +232,22 @@ __global__ void __maxnreg__(120) factor_reduce_kernel(const __grid_constant__ Li
   block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
+constexpr int kFactorRegs = 128;  // 4 CTAs x 128 threads x 128 registers = the whole register file, no spills (120 left 32 B on the stack)
+#ifdef SGB_PROFILING
+static int factor_regs_switch() {  // SGB_FACTOR_REGS=96 / 80: GICP without robust kernel only (the bench workload)
+  static const int v = std::getenv("SGB_FACTOR_REGS") ? std::atoi(std::getenv("SGB_FACTOR_REGS")) : kFactorRegs;
+  return v;
+}
+#endif
 template <int FACTOR, int ROBUST>
 static cudaError_t launch_factor(const LinParams& P, int grid, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
-  return launch_dependent(factor_reduce_kernel<FACTOR, ROBUST>, grid, kLinBlock, smem, st, P);
+#ifdef SGB_PROFILING
+  if (FACTOR == 2 && ROBUST == 0 && factor_regs_switch() == 96) return launch_dependent(factor_reduce_kernel<2, 0, 96>, grid, kLinBlock, smem, st, P);
+  if (FACTOR == 2 && ROBUST == 0 && factor_regs_switch() == 80) return launch_dependent(factor_reduce_kernel<2, 0, 80>, grid, kLinBlock, smem, st, P);
+  if (FACTOR == 2 && ROBUST == 0 && factor_regs_switch() == 120) return launch_dependent(factor_reduce_kernel<2, 0, 120>, grid, kLinBlock, smem, st, P);
+#endif
+  return launch_dependent(factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs>, grid, kLinBlock, smem, st, P);
 }
 
 // resident CTAs per SM of one instantiation (the grid is sized to exactly one wave: a partial second wave of this
@@ -242,9 +257,24 @@ static int factor_ctas_per_sm() {
   static int cached = 0;
   if (cached) return cached;
   const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
-  cudaFuncSetAttribute(factor_reduce_kernel<FACTOR, ROBUST>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<FACTOR, ROBUST>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+#ifdef SGB_PROFILING
+  if (FACTOR == 2 && ROBUST == 0 && (factor_regs_switch() == 96 || factor_regs_switch() == 80)) {
+    if (factor_regs_switch() == 96) {
+      cudaFuncSetAttribute(factor_reduce_kernel<2, 0, 96>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(factor_reduce_kernel<2, 0, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<2, 0, 96>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+    } else {
+      cudaFuncSetAttribute(factor_reduce_kernel<2, 0, 80>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(factor_reduce_kernel<2, 0, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<2, 0, 80>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+    }
+    cached = nb;
+    return nb;
+  }
+#endif
+  cudaFuncSetAttribute(factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
   cached = nb;
   return nb;
 }
