@@ -332,8 +332,11 @@ int do_error_impl(sgb_ctx* ctx, const double* T, double* d_out) {
     }
     return 0;
   }
+  // point targets: the factor kernel's operand pipeline (one wave of CTAs looping over tiles); voxel-map targets and the profiling switch
+  // SGB_ERROR_PIPE=0: the plain grid-stride kernel
+  const bool pipelined = !ctx->tgt_is_voxel && ctx->error_pipelined;
   int grid = static_cast<int>((ctx->n_src + kLinBlock - 1) / kLinBlock);
-  const int cap = ctx->sm_count * 8;
+  const int cap = ctx->sm_count * (pipelined ? error_pipelined_occupancy(ctx->lin_factor, ctx->lin_robust) : 8);
   if (grid > cap) grid = cap;
   if (int rc = ensure_reduction_buffers(ctx, grid)) return rc;
   LinParams P;
@@ -341,7 +344,10 @@ int do_error_impl(sgb_ctx* ctx, const double* T, double* d_out) {
   std::memcpy(P.Tlin, ctx->Tlin, sizeof(P.Tlin));
   P.robust_c = ctx->lin_c;
   P.out = d_out;
-  CU(launch_error(P, ctx->lin_factor, ctx->lin_robust, grid, ctx->stream));
+  if (pipelined)
+    CU(launch_error_pipelined(P, ctx->lin_factor, ctx->lin_robust, grid, ctx->stream));
+  else
+    CU(launch_error(P, ctx->lin_factor, ctx->lin_robust, grid, ctx->stream));
   ctx->launches += 1;
   return 0;
 }
@@ -463,6 +469,7 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_GRID_ORDER")) ctx->grid_curve_order = !(s[0] == '0');  // 0 = block lists in raster order of the packed block coordinates
   if (const char* s = getenv("SGB_RING_SCAN")) ctx->use_ring_scan = (s[0] == '1');  // 1 = many pending queries through the thread-per-query ring scan (rejected A/B)
   if (const char* s = getenv("SGB_KD_SMEM")) ctx->kd_smem_refine = !(s[0] == '0');  // 0 = kd refinement with one radix sort per level all the way down
+  if (const char* s = getenv("SGB_ERROR_PIPE")) ctx->error_pipelined = !(s[0] == '0');  // 0 = Reduction::error through the plain grid-stride kernel
   if (const char* s = getenv("SGB_TMA_LEAF")) ctx->tma_leaf = (s[0] == '1');  // 1 = dense leaf scans read a cp.async.bulk (TMA) staged copy of the leaf
   if (const char* s = getenv("SGB_CLASS_FALLBACK_PCT")) ctx->class_fallback_pct = static_cast<uint32_t>(std::max(0, atoi(s)));
   if (const char* s = getenv("SGB_CLASS_WIDE")) ctx->class_wide_cells = static_cast<float>(atof(s));

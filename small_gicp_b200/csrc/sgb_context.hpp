@@ -97,6 +97,7 @@ struct sgb_ctx {
   bool grid_curve_order = true;  // block lists laid out along a Morton curve (profiling switch SGB_GRID_ORDER=0: raster order of the packed coordinates)
   bool use_ring_scan = false;    // profiling switch SGB_RING_SCAN=1: many pending queries through a thread-per-query ring scan (measured: much slower)
   bool kd_smem_refine = true;    // subtrees of <= 2048 points refined in shared memory by one launch (profiling switch SGB_KD_SMEM=0: one radix sort per level)
+  bool error_pipelined = true;   // Reduction::error through the factor kernel's cp.async operand pipeline (profiling switch SGB_ERROR_PIPE=0: plain kernel)
   bool tma_leaf = false;         // profiling switch SGB_TMA_LEAF=1 (A/B of the north-star's TMA leaf staging)
   bool use_chunk_classes = true; // profiling switch SGB_CHUNK_CLASSES=0: the packet search scans all chunks in curve order
   int packet_parity = 0;

@@ -45,6 +45,9 @@ int search_occupancy(int stack_depth);
 cudaError_t launch_search(const LinParams& P, int grid, int stack_depth, cudaStream_t st);
 cudaError_t launch_factor_reduce(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
 int factor_reduce_occupancy(int factor, int robust);
+/// Reduction::error through the factor kernel's operand pipeline (one wave of CTAs looping over tiles)
+cudaError_t launch_error_pipelined(const LinParams& P, int factor, int robust, int grid, cudaStream_t st);
+int error_pipelined_occupancy(int factor, int robust);
 
 cudaError_t launch_bounds_centre(const double* d_pts4, size_t n, double* d_bounds6, double* d_centre4, int sm_count, cudaStream_t st);
 cudaError_t launch_convert(const double* d_pts4, const double* d_normals4, const double* d_covs16, size_t n, const double* d_centre4, float4* out_pts,

@@ -160,14 +160,18 @@ constexpr int kFactorStages = 3;
 
 // NREG: register budget per thread = resident CTAs per SM (128 -> 4 CTAs x 4 warps, no spills; 96 -> 5 CTAs; 80 -> 6, both with spills and slower): the algebra is a chain of
 // dependent FP64 operations and the kernel is short of warps, not of FP64 pipe (41 % active) -- A/B in profiles/r02/b_experiments.md.
-template <int FACTOR, int ROBUST, int NREG>
+// ERR: the same operand pipeline evaluating Reduction::error instead (cached correspondences, trial pose P.T, GICP precision matrix re-derived
+// from the linearisation pose P.Tlin, one sum): the LM inner loop's kernel.  The plain grid-stride version of it (error_kernel, sgb_kernels.cu)
+// waited on two dependent load round trips per point with nothing in flight: 48 us per 1M points against 38 us for the whole linearize algebra.
+template <int FACTOR, int ROBUST, int NREG, bool ERR = false>
 __global__ void __maxnreg__(NREG) factor_reduce_kernel(const __grid_constant__ LinParams P) {
   using F = FactorFields<FACTOR>;
   extern __shared__ float4 s_zone[];  // [kFactorStages][F::kAll][kLinBlock]
   __shared__ uint32_t s_corr[kFactorStages][kLinBlock];
-  double acc[kAcc + 1];
+  constexpr int NACC = ERR ? 1 : kAcc + 1;
+  double acc[NACC];
 #pragma unroll
-  for (int k = 0; k <= kAcc; k++) acc[k] = 0.0;
+  for (int k = 0; k < NACC; k++) acc[k] = 0.0;
   const double* R = P.T;
   const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
   const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
@@ -219,17 +223,22 @@ __global__ void __maxnreg__(NREG) factor_reduce_kernel(const __grid_constant__ L
     const uint32_t best = s_corr[st][tid];
     if (best != kNone) {
       const uint32_t i = tile * kLinBlock + tid;
-      // operands out of this thread's landing zone; the per-point arithmetic is point_linearize_source (sgb_math.cuh)
+      // operands out of this thread's landing zone; the per-point arithmetic is point_linearize_source / point_error (sgb_math.cuh)
       const float4 sp = *slot(st, 0);
       const float4 tq = *slot(st, F::kSrc);
-      if (!point_linearize_source<FACTOR, ROBUST>(R, tpx, tpy, tpz, csx, csy, csz, P.max_dist_sq_d, P.robust_c, sp, slot(st, 1), slot(st, 2), tq,
-                                                  slot(st, F::kSrc + 1), slot(st, F::kSrc + 2), acc))
+      if (ERR) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[0] += point_error<FACTOR, ROBUST>(R, tpx, tpy, tpz, P.Tlin, P.robust_c, sp, FACTOR == 2 ? *slot(st, 1) : z, FACTOR == 2 ? *slot(st, 2) : z, tq,
+                                              FACTOR >= 1 ? *slot(st, F::kSrc + 1) : z, FACTOR == 2 ? *slot(st, F::kSrc + 2) : z);
+      } else if (!point_linearize_source<FACTOR, ROBUST>(R, tpx, tpy, tpz, csx, csy, csz, P.max_dist_sq_d, P.robust_c, sp, slot(st, 1), slot(st, 2), tq,
+                                                         slot(st, F::kSrc + 1), slot(st, F::kSrc + 2), acc)) {
         P.corr[i] = kNone;  // rejected: error() and sgb_correspondences() must not see it
+      }
     }
     st = st1;
   }
   cp_async_wait_all();
-  block_reduce_and_finish<kAcc + 1, true>(acc, P.partials, P.ticket, P.out, P.comm);
+  block_reduce_and_finish<NACC, !ERR>(acc, P.partials, P.ticket, P.out, P.comm);
 }
 
 constexpr int kFactorRegs = 128;  // 4 CTAs x 128 threads x 128 registers = the whole register file, no spills (120 left 32 B on the stack)
@@ -248,6 +257,24 @@ static cudaError_t launch_factor(const LinParams& P, int grid, cudaStream_t st) 
   if (FACTOR == 2 && ROBUST == 0 && factor_regs_switch() == 120) return launch_dependent(factor_reduce_kernel<2, 0, 120>, grid, kLinBlock, smem, st, P);
 #endif
   return launch_dependent(factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs>, grid, kLinBlock, smem, st, P);
+}
+
+template <int FACTOR, int ROBUST>
+static cudaError_t launch_error_pipe(const LinParams& P, int grid, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
+  factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs, true><<<grid, kLinBlock, smem, st>>>(P);
+  return cudaGetLastError();
+}
+template <int FACTOR, int ROBUST>
+static int error_ctas_per_sm() {
+  static int cached = 0;
+  if (cached) return cached;
+  const size_t smem = static_cast<size_t>(kFactorStages) * FactorFields<FACTOR>::kAll * kLinBlock * sizeof(float4);
+  cudaFuncSetAttribute(factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs, true>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+  cached = nb;
+  return nb;
 }
 
 // resident CTAs per SM of one instantiation (the grid is sized to exactly one wave: a partial second wave of this
@@ -277,6 +304,27 @@ static int factor_ctas_per_sm() {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_reduce_kernel<FACTOR, ROBUST, kFactorRegs>, kLinBlock, smem) != cudaSuccess || nb < 1) nb = 1;
   cached = nb;
   return nb;
+}
+
+#define SGB_SPLIT_DISPATCH(FN, ...)                                \
+  switch (factor * 3 + robust) {                                   \
+    case 0: return FN<0, 0>(__VA_ARGS__);                          \
+    case 1: return FN<0, 1>(__VA_ARGS__);                          \
+    case 2: return FN<0, 2>(__VA_ARGS__);                          \
+    case 3: return FN<1, 0>(__VA_ARGS__);                          \
+    case 4: return FN<1, 1>(__VA_ARGS__);                          \
+    case 5: return FN<1, 2>(__VA_ARGS__);                          \
+    case 6: return FN<2, 0>(__VA_ARGS__);                          \
+    case 7: return FN<2, 1>(__VA_ARGS__);                          \
+    case 8: return FN<2, 2>(__VA_ARGS__);                          \
+  }
+cudaError_t launch_error_pipelined(const LinParams& P, int factor, int robust, int grid, cudaStream_t st) {
+  SGB_SPLIT_DISPATCH(launch_error_pipe, P, grid, st)
+  return cudaErrorInvalidValue;
+}
+int error_pipelined_occupancy(int factor, int robust) {
+  SGB_SPLIT_DISPATCH(error_ctas_per_sm)
+  return 1;
 }
 
 int factor_reduce_occupancy(int factor, int robust) {
