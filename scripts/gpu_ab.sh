@@ -8,7 +8,7 @@ for spec in "$@"; do
   name=${spec%%:*}; envs=${spec#*:}
   [ "$envs" = "$spec" ] && envs=""
   (
-    if [ "$name" != "product" ]; then export SGB_LIBRARY=prof; fi
+    if [ "${name#prev}" != "$name" ]; then export SGB_LIBRARY=prev; elif [ "${name#product}" = "$name" ]; then export SGB_LIBRARY=prof; fi
     IFS=',' read -ra kv <<< "$envs"
     for e in "${kv[@]}"; do [ -n "$e" ] && export "$e"; done
     timeout 300 python bench.py --steps 40 --warmup 5 --no-extras --no-cpu-baseline > $OUT/$name.json 2> $OUT/$name.err

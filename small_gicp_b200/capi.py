@@ -65,6 +65,8 @@ class SgbError(RuntimeError):
 def library_path(profiling=False):
     """the product library; profiling=True: the same sources built with -DSGB_PROFILING (experiment switches read from SGB_*
     environment variables in sgb_create + the superseded A/B kernels) -- A/B scripts and the structure-agreement test only"""
+    if os.environ.get("SGB_LIBRARY", "") == "prev" and not profiling:  # A/B against a saved build of the product library (scripts/gpu_ab.sh)
+        return os.path.join(_HERE, "lib", "libsgicp_b200_prev.so")
     return os.path.join(_HERE, "lib", "libsgicp_b200_prof.so" if profiling else "libsgicp_b200.so")
 
 

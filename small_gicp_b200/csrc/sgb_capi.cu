@@ -238,7 +238,7 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
           cc.fallback_pct = ctx->class_fallback_pct;
         }
         CU(ctx->grid_pending_q.reserve(ctx->n_src * sizeof(float4)));
-        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_blocks, ctx->probe_batch_tail, ctx->grid_state.as<uint8_t>(), pc,
+        CU(launch_grid_probe(P, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), ctx->grid_capacity, g, ctx->grid_state.as<uint8_t>(), pc,
                              plist, ctx->grid_pending_q.as<float4>(), pbase + (ctx->pending_parity ^ 1), cc, ctx->stream));
         ctx->pending_parity ^= 1;
         // the finishing kernel (below) serves both regimes: few pending queries warp-per-query, many through the packet walk
@@ -252,16 +252,8 @@ int do_linearize_impl(sgb_ctx* ctx, int factor, int robust, double robust_c, int
         settled = ctx->grid_state.as<uint8_t>();
         pending_count = pc;
       }
-      // Many pending queries: the packet search walks the tree.  (Profiling build, SGB_RING_SCAN=1: when the rejector's radius lies inside
-      // what the 27-block ring covers, a thread per pending query finishes them from the block lists instead -- measured 1.5 - 1.7x slower.)
-      const bool ring_scan = ctx->use_ring_scan && ctx->grid_ready && ctx->grid_blocks && ctx->use_ring && bound <= ring_cover_sq(ctx->grid_cell);
-      if (ring_scan) {
-        const int rgrid = static_cast<int>(std::min<size_t>((ctx->n_src + 255) / 256, static_cast<size_t>(ctx->sm_count) * 8));
-        pp.few_only = true;  // the finishing kernel still serves the few-pending regime
-        CU(launch_ring_scan(P, pending_count, ctx->grid_pending.as<uint32_t>() + 2, pending_split, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(),
-                            ctx->grid_capacity, pp.g, rgrid, ctx->stream));
-        CU(launch_packet_search(P, ctx->tgt_pnodes.as<float4>(), sgrid, depth, settled, pending_count, pending_split, nullptr, nullptr, ChunkClasses{}, pp, false, ctx->stream));
-      } else {
+      // many pending queries: the packet search walks the tree
+      {
       uint32_t *queue = nullptr, *queue_next = nullptr;
       if (ctx->use_packet_queue) {
         if (!ctx->packet_queue.p) {  // first use: two zeroed counters (afterwards every launch clears the other one)
@@ -456,18 +448,15 @@ int sgb_create(int device_id, sgb_ctx** out_ctx) {
   if (const char* s = getenv("SGB_CURVE")) set_source_curve(atoi(s));     // profiling switch: 0 Morton, 1 Hilbert (default)
   if (const char* s = getenv("SGB_GRID")) ctx->use_grid = !(s[0] == '0');  // profiling switch: 0 = tree search only
   // profiling switches of the grid front end (A/B runs in profiles/, variants exercised by tests/test_gpu_parity.py)
-  if (const char* s = getenv("SGB_GRID_BLOCKS")) ctx->grid_blocks_wanted = !(s[0] == '0');  // 0 = per-cell lists, eight lookups per query
   if (const char* s = getenv("SGB_RING")) ctx->use_ring = !(s[0] == '0');                   // 0 = pending queries always walk the tree
   if (const char* s = getenv("SGB_PENDING_DIV")) ctx->pending_div = std::max(1, atoi(s));   // packet search when more than n / div queries are pending
   if (const char* s = getenv("SGB_GRID_CELL")) {                                            // cell edge in units of the median point spacing
     const double v = atof(s);
     if (v > 0.1 && v < 100.0) ctx->grid_cell_factor = v;
   }
-  if (const char* s = getenv("SGB_PROBE_TAIL")) ctx->probe_batch_tail = (s[0] == '1');        // 1 = probe scans its list in clamped batches of eight (A/B, sgb_grid.cu)
   if (const char* s = getenv("SGB_PACKET_QUEUE")) ctx->use_packet_queue = !(s[0] == '0');   // 0 = chunks assigned to warps by a static stride
   if (const char* s = getenv("SGB_CHUNK_CLASSES")) ctx->use_chunk_classes = !(s[0] == '0');  // 0 = no work lists by cost class: chunks in curve order
   if (const char* s = getenv("SGB_GRID_ORDER")) ctx->grid_curve_order = !(s[0] == '0');  // 0 = block lists in raster order of the packed block coordinates
-  if (const char* s = getenv("SGB_RING_SCAN")) ctx->use_ring_scan = (s[0] == '1');  // 1 = many pending queries through the thread-per-query ring scan (rejected A/B)
   if (const char* s = getenv("SGB_KD_SMEM")) ctx->kd_smem_refine = !(s[0] == '0');  // 0 = kd refinement with one radix sort per level all the way down
   if (const char* s = getenv("SGB_ERROR_PIPE")) ctx->error_pipelined = !(s[0] == '0');  // 0 = Reduction::error through the plain grid-stride kernel
   if (const char* s = getenv("SGB_TMA_LEAF")) ctx->tma_leaf = (s[0] == '1');  // 1 = dense leaf scans read a cp.async.bulk (TMA) staged copy of the leaf

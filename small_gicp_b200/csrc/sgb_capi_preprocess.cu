@@ -109,14 +109,12 @@ int build_grid(sgb_ctx* ctx) {
   g.inv_cell = static_cast<float>(1.0 / cell);
   const double settle = (0.5 - 4e-3) * cell;  // margin for the FP32 cell-coordinate arithmetic (kGridSlack cells, sgb_grid.cu)
   g.settle_d2 = static_cast<float>(settle * settle);
-  const bool blocks = ctx->grid_blocks_wanted;
-  const size_t n_ent = blocks ? n * 8 : n;  // block lists hold every point under its eight enclosing 2 x 2 x 2 blocks
+  const size_t n_ent = n * 8;  // block lists hold every point under its eight enclosing 2 x 2 x 2 blocks
   if (n_ent >= (1ull << 31)) return 0;
   CU(ctx->keys_in.reserve(n_ent * sizeof(uint64_t)));
   CU(ctx->keys_out.reserve(n_ent * sizeof(uint64_t)));
   CU(ctx->vals_in.reserve(n_ent * sizeof(uint32_t)));
   CU(ctx->pre_vals_out.reserve(n_ent * sizeof(uint32_t)));
-  CU(ctx->grid_pts.reserve(n_ent * sizeof(float4)));
   CU(ctx->grid_pending.reserve(2 * sizeof(uint32_t)));
   size_t tb = 0;
   CU(sort_pairs_u64_u32(nullptr, tb, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), n_ent,
@@ -124,7 +122,7 @@ int build_grid(sgb_ctx* ctx) {
   CU(ctx->sort_temp.reserve(tb));
   uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the two pending counters double as scratch during construction
   uint32_t* d_max_list = d_distinct + 1;
-  CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, blocks, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+  CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
                       ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->grid_curve_order, ctx->stream));
   uint32_t distinct = 0;
   CU(cudaMemcpyAsync(&distinct, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream));
@@ -132,9 +130,12 @@ int build_grid(sgb_ctx* ctx) {
   uint32_t capacity = 1024;
   while (capacity < 2ull * distinct) capacity <<= 1;  // load factor <= 1/2
   CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
-  CU(launch_grid_fill(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n_ent),
-                      ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, d_max_list, ctx->grid_curve_order, ctx->stream));
-  ctx->grid_blocks = blocks;
+  // lists are stored as pair records (two points each, sgb_grid.cuh): a list of odd length carries one pad
+  CU(ctx->grid_pts.reserve((n_ent + distinct + 2) * sizeof(float4)));
+  CU(launch_grid_fill(ctx->keys_out.as<uint64_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n_ent), ctx->vals_in.as<uint32_t>(),
+                      ctx->keys_in.as<uint32_t>(), ctx->sort_temp.p, tb, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->grid_curve_order,
+                      ctx->stream));
+  ctx->grid_blocks = true;
   ctx->pending_clean = false;  // d_distinct / d_max_list live in the pending counters
   ctx->launches += 9;
   uint32_t max_list = 0;

@@ -83,7 +83,7 @@ struct sgb_ctx {
   bool use_grid = true, grid_ready = false, grid_blocks = true;  // grid_blocks: 2 x 2 x 2 block lists (one lookup per query) instead of per-cell lists
   sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0], [1] = alternating counters, [2..] = pending query positions
   sgb::DevBuf grid_pending_q;  // parallel to the list: transformed query + squared distance of the probe's best candidate
-  bool grid_blocks_wanted = true, use_ring = true, debug_pending = false;  // profiling switches (sgb_create)
+  bool use_ring = true, debug_pending = false;  // profiling switches (sgb_create)
   int pending_div = 16;           // more than n_src / pending_div pending queries: packet search, else a warp per pending query
   double grid_cell_factor = 2.5;  // cell edge in units of the median point spacing (sweep in profiles/r01: 2 / 2.5 / 3 / 4)
   uint32_t grid_capacity = 0;
@@ -95,14 +95,12 @@ struct sgb_ctx {
   uint32_t class_fallback_pct = 85;  // more than this share of the chunks listed (pending lanes almost everywhere): curve order instead of the lists
   float class_wide_cells = 2.0f;     // search radius (in cells) from which a chunk counts as wide
   bool grid_curve_order = true;  // block lists laid out along a Morton curve (profiling switch SGB_GRID_ORDER=0: raster order of the packed coordinates)
-  bool use_ring_scan = false;    // profiling switch SGB_RING_SCAN=1: many pending queries through a thread-per-query ring scan (measured: much slower)
   bool kd_smem_refine = true;    // subtrees of <= 2048 points refined in shared memory by one launch (profiling switch SGB_KD_SMEM=0: one radix sort per level)
   bool error_pipelined = true;   // Reduction::error through the factor kernel's cp.async operand pipeline (profiling switch SGB_ERROR_PIPE=0: plain kernel)
   bool tma_leaf = false;         // profiling switch SGB_TMA_LEAF=1 (A/B of the north-star's TMA leaf staging)
   bool use_chunk_classes = true; // profiling switch SGB_CHUNK_CLASSES=0: the packet search scans all chunks in curve order
   int packet_parity = 0;
   bool use_packet_queue = true;  // profiling switch SGB_PACKET_QUEUE=0: static stride
-  bool probe_batch_tail = false; // A/B switch SGB_PROBE_TAIL=1: block-list scan in clamped batches of eight (measured: no gain)
   float grid_origin[3] = {0, 0, 0}, grid_inv_cell = 1.f, grid_settle_d2 = 0.f, grid_cell = 0.f;
   sgb::DevBuf tgt_centre, tgt_bounds;  // 4 / 6 doubles
   sgb::DevBuf vox_table;

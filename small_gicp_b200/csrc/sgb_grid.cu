@@ -63,10 +63,9 @@ __device__ __forceinline__ uint64_t grid_table_key(uint64_t k, bool curve) {
 // cell key of every target point (leaf-ordered, centred FP32); value = leaf position.
 // BLOCKS: every point is entered under the eight 2 x 2 x 2 cell blocks that contain its cell (block anchor = lowest cell),
 // so that a query finds every point of the block around it in ONE contiguous run (8x the points, one lookup, one loop).
-template <bool BLOCKS>
 __global__ void grid_keys_kernel(const float4* __restrict__ pts, uint32_t n, GridParams g, uint64_t* keys, uint32_t* vals, bool curve) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t i = BLOCKS ? t >> 3 : t, o = BLOCKS ? t & 7u : 0u;
+  const uint32_t i = t >> 3, o = t & 7u;
   if (i >= n) return;
   const float4 p = pts[i];
   const int ix = __float2int_rd((p.x - g.origin[0]) * g.inv_cell), iy = __float2int_rd((p.y - g.origin[1]) * g.inv_cell),
@@ -75,37 +74,61 @@ __global__ void grid_keys_kernel(const float4* __restrict__ pts, uint32_t n, Gri
   vals[t] = i;
 }
 
-// number of distinct keys of the sorted key array (sizes the hash table)
-__global__ void grid_count_heads_kernel(const uint64_t* __restrict__ keys, uint32_t m, uint32_t* count) {
+// after the sort: one table entry per run of equal keys, and the run's points as PAIR RECORDS (sgb_grid.cuh: GridPair).
+// pass 1 (heads): length of every run -> its number of records at the head's position (0 elsewhere); counters[0] = number of runs
+// (sizes the hash table and, with m, the record array), counters[1] = longest run
+__global__ void grid_heads_kernel(const uint64_t* __restrict__ keys, uint32_t m, uint32_t* pairs, uint32_t* counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool head = i < m && (i == 0 || keys[i - 1] != keys[i]);
-  const unsigned b = __ballot_sync(0xffffffffu, head);
-  if ((threadIdx.x & 31u) == 0 && b) atomicAdd(count, static_cast<uint32_t>(__popc(b)));
-}
-
-// after the sort: gather the points into cell order (w = leaf position) and insert one table entry per run of equal keys
-__global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ leaf_pos, const float4* __restrict__ leaf_pts, uint32_t n,
-                                 float4* grid_pts, GridSlot* table, uint32_t mask, uint32_t* max_count, bool curve) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t lp = leaf_pos[i];
-  const float4 p = leaf_pts[lp];
-  grid_pts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(lp));
-  const uint64_t k = keys[i];
-  if (i == 0 || keys[i - 1] != k) {  // head of a cell: count its points, claim a slot
-    uint32_t cnt = 1;
-    while (i + cnt < n && keys[i + cnt] == k) cnt++;
-    const uint64_t tk = grid_table_key(k, curve);
-    uint32_t slot = grid_hash_of_key(tk) & mask;
-    for (;;) {
-      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), ~0ull, static_cast<unsigned long long>(tk));
-      if (prev == ~0ull) break;
-      slot = (slot + 1u) & mask;
+  uint32_t np = 0;
+  bool head = false;
+  if (i < m) {
+    const uint64_t k = keys[i];
+    head = i == 0 || keys[i - 1] != k;
+    if (head) {
+      uint32_t cnt = 1;
+      while (i + cnt < m && keys[i + cnt] == k) cnt++;
+      np = (cnt + 1u) >> 1;
+      atomicMax(counters + 1, cnt);  // longest list: build_grid drops the front end when one query would have to scan thousands of points
     }
-    table[slot].start = i;
-    table[slot].count = cnt;
-    atomicMax(max_count, cnt);  // longest list: build_grid drops the front end when one query would have to scan thousands of points
+    pairs[i] = np;
   }
+  const unsigned b = __ballot_sync(0xffffffffu, head);
+  if ((threadIdx.x & 31u) == 0 && b) atomicAdd(counters, static_cast<uint32_t>(__popc(b)));
+}
+// pass 2 (after an exclusive scan of `pairs` -> first record of every run): the head of a run writes its records -- two points per
+// record, components interleaved; an odd run is padded with a point at infinity that can never be nearest -- and claims the table slot
+__global__ void grid_fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ leaf_pos, const float4* __restrict__ leaf_pts, uint32_t m,
+                                 const uint32_t* __restrict__ pair_start, GridPair* grid_pairs, GridSlot* table, uint32_t mask, bool curve) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t k = keys[i];
+  if (i != 0 && keys[i - 1] == k) return;
+  uint32_t cnt = 1;
+  while (i + cnt < m && keys[i + cnt] == k) cnt++;
+  const uint32_t first = pair_start[i];
+  for (uint32_t e = 0; e < cnt; e += 2u) {
+    const uint32_t l0 = leaf_pos[i + e];
+    const float4 p0 = leaf_pts[l0];
+    float4 p1 = make_float4(kGridPadCoord, kGridPadCoord, kGridPadCoord, 0.f);
+    uint32_t l1 = kNone;
+    if (e + 1u < cnt) {
+      l1 = leaf_pos[i + e + 1u];
+      p1 = leaf_pts[l1];
+    }
+    GridPair r;
+    r.a = make_float4(p0.x, p1.x, p0.y, p1.y);
+    r.b = make_float4(p0.z, p1.z, __uint_as_float(l0), __uint_as_float(l1));
+    grid_pairs[first + (e >> 1)] = r;
+  }
+  const uint64_t tk = grid_table_key(k, curve);
+  uint32_t slot = grid_hash_of_key(tk) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), ~0ull, static_cast<unsigned long long>(tk));
+    if (prev == ~0ull) break;
+    slot = (slot + 1u) & mask;
+  }
+  table[slot].start = first;  // in records
+  table[slot].count = cnt;    // in points
 }
 
 __global__ void grid_table_init_kernel(GridSlot* table, uint32_t capacity) {
@@ -117,114 +140,6 @@ __global__ void grid_table_init_kernel(GridSlot* table, uint32_t capacity) {
   }
 }
 
-__device__ __forceinline__ void grid_scan(const float4* __restrict__ cp, uint32_t cnt, float fx, float fy, float fz, float& best_d, uint32_t& best) {
-#pragma unroll 4
-  for (uint32_t j = 0; j < cnt; j++) {
-    const float4 t = __ldg(&cp[j]);
-    const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-    const float d = dx * dx + dy * dy + dz * dz;
-    if (d < best_d) {
-      best_d = d;
-      best = __float_as_uint(t.w);
-    }
-  }
-}
-
-#ifdef SGB_PROFILING  // per-cell lists, eight lookups per query (SGB_GRID_BLOCKS=0): superseded by the block lists, kept for A/B runs only
-// ---------------------------------------------------------------------------------------------------------------
-// probe: one query per thread (Hilbert order -> neighbouring lanes hit neighbouring cells)
-// state[i] = 1: settled (corr[i] is the exact nearest neighbour), 0: pending for the tree search (corr[i] = best candidate)
-// ---------------------------------------------------------------------------------------------------------------
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
-                                                           const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell_sq, uint8_t* state,
-                                                           uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count) {
-  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = gi < P.src.n;
-  if (gi == 0u) *next_count = 0u;  // the counter of the NEXT linearize (two counters alternate: no memset between launches)
-  const uint32_t i = in_range ? gi : P.src.n - 1u;  // out-of-range lanes shadow the last query (no divergent exit before the warp vote below)
-  const double* R = P.T;
-  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
-  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
-  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
-  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
-  const float4 s = __ldg(&P.src.pts[i]);
-  const double sx = s.x, sy = s.y, sz = s.z;
-  const float fx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
-  const float fy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
-  const float fz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
-
-  float best_d = P.max_dist_sq;
-  uint32_t best = kNone;
-  // own cell, and per axis the neighbour on the side the query leans to: together the 2 x 2 x 2 block around [q - c/2, q + c/2]^3
-  const float ux = (fx - g.origin[0]) * g.inv_cell, uy = (fy - g.origin[1]) * g.inv_cell, uz = (fz - g.origin[2]) * g.inv_cell;
-  const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-  // queries far outside the target's box cannot be settled anyway; clamping keeps the integer cell coordinates in range
-  const int ox = static_cast<int>(fminf(fmaxf(flx, -1e5f), 1e5f)), oy = static_cast<int>(fminf(fmaxf(fly, -1e5f), 1e5f)),
-            oz = static_cast<int>(fminf(fmaxf(flz, -1e5f), 1e5f));
-  const float frx = ux - flx, fry = uy - fly, frz = uz - flz;
-  const int nx = frx >= 0.5f ? 1 : -1, ny = fry >= 0.5f ? 1 : -1, nz = frz >= 0.5f ? 1 : -1;
-  // squared distance (cell units, less the rounding slack) to the neighbour cell's slab along each axis
-  const float ax = fmaxf((frx >= 0.5f ? 1.0f - frx : frx) - kGridSlack, 0.0f), ay = fmaxf((fry >= 0.5f ? 1.0f - fry : fry) - kGridSlack, 0.0f),
-              az = fmaxf((frz >= 0.5f ? 1.0f - frz : frz) - kGridSlack, 0.0f);
-  const float ax2 = ax * ax * cell_sq, ay2 = ay * ay * cell_sq, az2 = az * az * cell_sq;
-  // all eight table lookups first: eight independent loads in flight, no divergence (the first slot of each probe
-  // sequence is fetched unconditionally; collisions are resolved below)
-  uint4 ent[8];
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const int ix = ox + ((c & 1) ? nx : 0), iy = oy + ((c & 2) ? ny : 0), iz = oz + ((c & 4) ? nz : 0);
-    ent[c] = __ldg(reinterpret_cast<const uint4*>(&table[grid_hash(ix, iy, iz) & mask]));
-  }
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    // the own cell first, then the neighbours whose box is still closer than the best distance so far
-    const float bd = ((c & 1) ? ax2 : 0.f) + ((c & 2) ? ay2 : 0.f) + ((c & 4) ? az2 : 0.f);
-    if (!(bd < best_d)) continue;
-    const int ix = ox + ((c & 1) ? nx : 0), iy = oy + ((c & 2) ? ny : 0), iz = oz + ((c & 4) ? nz : 0);
-    const uint64_t key = grid_key(ix, iy, iz);
-    uint4 e = ent[c];
-    uint64_t ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
-    uint32_t slot = grid_hash(ix, iy, iz) & mask;
-    while (ek != key && ek != ~0ull) {  // rare: the table is sparsely filled
-      slot = (slot + 1u) & mask;
-      e = __ldg(reinterpret_cast<const uint4*>(&table[slot]));
-      ek = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
-    }
-    if (ek == key) grid_scan(grid_pts + e.z, e.w, fx, fy, fz, best_d, best);
-  }
-  const bool settled = best != kNone && best_d <= g.settle_d2;
-  if (!settled && P.use_prev) {  // keep the better of (grid candidate, previous correspondence) as the tree search's seed
-    const uint32_t prev = P.corr[i];
-    if (prev != kNone && best == kNone) best = prev;
-    else if (prev != kNone) {
-      const float4 t = __ldg(&P.tgt.pts[prev]);
-      const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-      if (dx * dx + dy * dy + dz * dz < best_d) best = prev;
-    }
-  }
-  if (in_range) {
-    P.corr[i] = best;
-    state[i] = settled ? 1 : 0;
-  }
-  // pending queries go to a compact work list (warp-aggregated append)
-  const bool pend = in_range && !settled;
-  const unsigned m = __ballot_sync(0xffffffffu, pend);
-  if (m) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == static_cast<uint32_t>(__ffs(m) - 1)) base = atomicAdd(pending_count, static_cast<uint32_t>(__popc(m)));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (pend) {
-      const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
-      pending_list[slot] = i;
-      pending_q[slot] = make_float4(fx, fy, fz, (best == kNone || !(best_d < P.max_dist_sq)) ? P.max_dist_sq : best_d);
-    }
-  }
-}
-
-#endif  // SGB_PROFILING
-
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
 // ---------------------------------------------------------------------------------------------------------------
@@ -232,8 +147,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_kernel(const __grid_
 // remainder loop of count % 8 iterations with ONE load in flight each -- 15 % of the kernel's stall samples sit on that
 // load's first use (profiles/r01/am).  The batched form always issues eight loads, clamping the index to the last point of
 // the list: a repeated point can never be strictly closer than itself, so the result is unchanged.
-template <int MIN_CTAS, bool BATCH_TAIL>
-__global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const float4* __restrict__ grid_pts,
+template <int MIN_CTAS, int UNROLL = 2, bool PREFETCH = true>
+__global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const GridPair* __restrict__ grid_pairs,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
                                                                uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count,
                                                                ChunkClasses cc) {
@@ -261,39 +176,31 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
             bz = static_cast<int>(fminf(fmaxf(az, -1e5f), 1e5f));
   const uint2 e = grid_lookup(table, mask, bx, by, bz);
   {
-    // the list is a contiguous run of e.y points: pull all of its lines into L2 at once (the scan below would otherwise
-    // pay one DRAM round trip per batch of loads: profiles/r01/q, 29 warps stalled on the scoreboard per issue)
-    const char* lp = reinterpret_cast<const char*>(grid_pts + e.x);
-    const uint32_t bytes = e.y * 16u;
-    for (uint32_t off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + off));
-    if (bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + bytes - 16u));  // last line of a run that is not 128 B aligned
-    const float4* __restrict__ cp = grid_pts + e.x;
-    if (BATCH_TAIL) {
-      const uint32_t last = e.y - 1u;  // only used when e.y > 0
-      for (uint32_t base = 0; base < e.y; base += 8u) {
-        float4 t[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = __ldg(&cp[min(base + static_cast<uint32_t>(u), last)]);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const float dx = t[u].x - fx, dy = t[u].y - fy, dz = t[u].z - fz;
-          const float d = dx * dx + dy * dy + dz * dz;
-          if (d < best_d) {
-            best_d = d;
-            best = __float_as_uint(t[u].w);
-          }
-        }
+    // The list is a contiguous run of ceil(e.y / 2) PAIR RECORDS (32 B: two points, components interleaved).  One 256-bit load
+    // (ld.global.nc.v8.f32 -> LDG.E.256, new with sm_100) brings a pair, and the squared distances of both points come out of packed FP32
+    // arithmetic (add / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2, also new with sm_100): half the load instructions -- the scan is bound by
+    // L1 wavefronts, ~11 distinct lists per warp and instruction (profiles/r02/f: l1tex 65 % busy) -- and half the arithmetic per point.
+    const GridPair* __restrict__ rec = grid_pairs + e.x;
+    const uint32_t npairs = (e.y + 1u) >> 1;
+    // pull all of its lines into L2 at once (the scan would otherwise pay one DRAM round trip per batch of loads)
+    const char* lp = reinterpret_cast<const char*>(rec);
+    const uint32_t bytes = npairs * 32u;
+    if (PREFETCH)
+      for (uint32_t off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + off));
+    if (PREFETCH && bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + bytes - 32u));  // last line of a run that is not 128 B aligned
+    const float2 nfx = make_float2(-fx, -fx), nfy = make_float2(-fy, -fy), nfz = make_float2(-fz, -fz);
+#pragma unroll UNROLL
+    for (uint32_t j = 0; j < npairs; j++) {
+      const GridPair t = load_pair(rec + j);
+      const float2 dx = __fadd2_rn(make_float2(t.a.x, t.a.y), nfx), dy = __fadd2_rn(make_float2(t.a.z, t.a.w), nfy), dz = __fadd2_rn(make_float2(t.b.x, t.b.y), nfz);
+      const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+      if (d.x < best_d) {  // first point of the pair first: ties keep the scan order
+        best_d = d.x;
+        best = __float_as_uint(t.b.z);
       }
-    } else {
-#pragma unroll 8
-      for (uint32_t j = 0; j < e.y; j++) {
-        const float4 t = __ldg(&cp[j]);
-        const float dx = t.x - fx, dy = t.y - fy, dz = t.z - fz;
-        const float d = dx * dx + dy * dy + dz * dz;
-        if (d < best_d) {
-          best_d = d;
-          best = __float_as_uint(t.w);
-        }
+      if (d.y < best_d) {  // (the pad of an odd list sits at 1e18: ~3e36, never nearest)
+        best_d = d.y;
+        best = __float_as_uint(t.b.w);
       }
     }
   }
@@ -367,88 +274,6 @@ __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const 
   }
 }
 
-#ifdef SGB_PROFILING
-// ---------------------------------------------------------------------------------------------------------------
-// Many pending queries AND a rejector whose radius the ring covers (DistanceRejector(1 m) with the usual cell: 2.5 c = 1.1 m): one THREAD
-// per pending query finishes it exactly from the block lists alone -- the 26 blocks at stride 2 around its own one (which the probe has
-// already scanned), each skipped when its box lies beyond the best distance so far.  Everything within sqrt(max_dist_sq) of the query is
-// inside those 27 blocks, so whatever is nearest there is the exact nearest neighbour, or provably nothing is in range.  The idea: trade
-// the packet walk's ~3,350 warp instructions per 32-query chunk for per-thread scans as wide as each query's own search ball.
-// MEASURED AND REJECTED (r02m, SGB_RING_SCAN=1): 0.417 vs 0.241 ms at the identity pose, 0.275 vs 0.181 ms at T1 -- up to 26 dependent
-// lookup + scan round trips per thread with neighbouring lanes needing different blocks is far slower than one shared, divergence-free
-// walk.  Exact (test_search_structures_agree: device-kd/grid-ring-scan-pending); profiling library only.
-// ---------------------------------------------------------------------------------------------------------------
-// the 26 neighbours of the centre block, faces first, then edges, then corners; ox | oy << 2 | oz << 4 with o in {0, 1, 2} = {-1, 0, +1}
-__constant__ unsigned char kRingOrder[26] = {
-  0x14, 0x16, 0x11, 0x19, 0x05, 0x25,                                                  // faces:  x-, x+, y-, y+, z-, z+
-  0x10, 0x12, 0x18, 0x1a, 0x04, 0x06, 0x24, 0x26, 0x01, 0x09, 0x21, 0x29,            // edges:  xy (4), xz (4), yz (4)
-  0x00, 0x02, 0x08, 0x0a, 0x20, 0x22, 0x28, 0x2a};                                    // corners
-__global__ void __launch_bounds__(256, 4) ring_scan_kernel(const __grid_constant__ LinParams P, const uint32_t* __restrict__ pending_count,
-                                                           const uint32_t* __restrict__ pending_list, uint32_t min_pending, const float4* __restrict__ grid_pts,
-                                                           const GridSlot* __restrict__ table, uint32_t mask, GridParams g, float cell) {
-  grid_dependency_wait();  // probe (and the warp-per-query kernel, which exits at once in this regime) wrote corr[] and the pending list
-  const uint32_t count = *pending_count;
-  if (count <= min_pending) return;
-  const double* R = P.T;
-  const double csx = P.src.centre[0], csy = P.src.centre[1], csz = P.src.centre[2];
-  const double tpx = R[0] * csx + R[1] * csy + R[2] * csz + P.T[9] - P.tgt.centre[0];
-  const double tpy = R[3] * csx + R[4] * csy + R[5] * csz + P.T[10] - P.tgt.centre[1];
-  const double tpz = R[6] * csx + R[7] * csy + R[8] * csz + P.T[11] - P.tgt.centre[2];
-  const float cell_sq = cell * cell;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-    const uint32_t i = pending_list[k];
-    const float4 s = __ldg(&P.src.pts[i]);
-    const double sx = s.x, sy = s.y, sz = s.z;
-    const float qx = static_cast<float>(R[0] * sx + R[1] * sy + R[2] * sz + tpx);
-    const float qy = static_cast<float>(R[3] * sx + R[4] * sy + R[5] * sz + tpy);
-    const float qz = static_cast<float>(R[6] * sx + R[7] * sy + R[8] * sz + tpz);
-    float best_d = P.max_dist_sq;
-    uint32_t best = P.corr[i];  // the probe's candidate (own block, or the previous correspondence): an upper bound
-    if (best != kNone) {
-      const float4 t = __ldg(&P.tgt.pts[best]);
-      const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-      const float d = dx * dx + dy * dy + dz * dz;
-      if (d < best_d) best_d = d;
-      else best = kNone;  // beyond the rejector's bound: no use
-    }
-    const float ux = (qx - g.origin[0]) * g.inv_cell, uy = (qy - g.origin[1]) * g.inv_cell, uz = (qz - g.origin[2]) * g.inv_cell;
-    const int ax = static_cast<int>(fminf(fmaxf(floorf(ux - 0.5f), -1e5f), 1e5f)), ay = static_cast<int>(fminf(fmaxf(floorf(uy - 0.5f), -1e5f), 1e5f)),
-              az = static_cast<int>(fminf(fmaxf(floorf(uz - 0.5f), -1e5f), 1e5f));
-    // per axis: squared distance (cell units, less the rounding slack) from the query to the lower / own / upper block slab
-    // (the query sits inside its own slab, so that distance is zero; scalars, not arrays: dynamic indexing would go to local memory)
-    auto slab = [&](float u, int a, int o) {
-      const float l = static_cast<float>(a + 2 * (o - 1));
-      const float f = fmaxf(fmaxf(l - u, u - (l + 2.0f)) - kGridSlack, 0.0f);
-      return f * f * cell_sq;
-    };
-    const float ex0 = slab(ux, ax, 0), ex2 = slab(ux, ax, 2), ey0 = slab(uy, ay, 0), ey2 = slab(uy, ay, 2), ez0 = slab(uz, az, 0), ez2 = slab(uz, az, 2);
-    // nearer blocks first: faces, then edges, then corners of the 3 x 3 x 3 arrangement (the centre is the probe's own block)
-    {
-#pragma unroll 1
-      for (int b = 0; b < 26; b++) {
-        const int code = kRingOrder[b], ox = code & 3, oy = (code >> 2) & 3, oz = code >> 4;
-        const float bd = (ox == 0 ? ex0 : (ox == 2 ? ex2 : 0.0f)) + (oy == 0 ? ey0 : (oy == 2 ? ey2 : 0.0f)) + (oz == 0 ? ez0 : (oz == 2 ? ez2 : 0.0f));
-        if (!(bd < best_d)) continue;
-        const uint2 e = grid_lookup(table, mask, ax + 2 * (ox - 1), ay + 2 * (oy - 1), az + 2 * (oz - 1));
-        const float4* __restrict__ cp = grid_pts + e.x;
-#pragma unroll 4
-        for (uint32_t j = 0; j < e.y; j++) {
-          const float4 t = __ldg(&cp[j]);
-          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-          const float d = dx * dx + dy * dy + dz * dz;
-          if (d < best_d) {
-            best_d = d;
-            best = __float_as_uint(t.w);
-          }
-        }
-      }
-    }
-    P.corr[i] = best;
-  }
-}
-
-#endif  // SGB_PROFILING
-
 // per-leaf spacing estimate from the packet records (two largest box extents / count) for the choice of the cell size
 __global__ void grid_spacing_kernel(const float4* __restrict__ pnodes, uint32_t n_inner, float* out) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -472,70 +297,54 @@ cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* o
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
-                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, bool curve, cudaStream_t st) {
-  const uint32_t m = blocks ? n * 8u : n;
-  if (blocks)
-    grid_keys_kernel<true><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in, curve);
-  else
-    grid_keys_kernel<false><<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in, curve);
+cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
+                             void* sort_temp, size_t sort_temp_bytes, uint32_t* d_counters, bool curve, cudaStream_t st) {
+  const uint32_t m = n * 8u;
+  grid_keys_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(leaf_pts, n, g, keys_in, vals_in, curve);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(m), 0, 63, st);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(d_distinct, 0, sizeof(uint32_t), st);
+  e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
-  grid_count_heads_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_out, m, d_distinct);
+  grid_heads_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_out, m, vals_in, d_counters);  // the sort's value input is free again: records per run
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
-                             uint32_t capacity, uint32_t* d_max_count, bool curve, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(d_max_count, 0, sizeof(uint32_t), st);
+cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, const uint32_t* pairs, uint32_t* pair_start,
+                             void* scan_temp, size_t scan_temp_bytes, float4* grid_pts, GridSlot* table, uint32_t capacity, bool curve, cudaStream_t st) {
+  size_t need = 0;
+  cudaError_t e = exclusive_sum_u32(nullptr, need, pairs, pair_start, m, st);
+  if (e != cudaSuccess) return e;
+  if (need > scan_temp_bytes) return cudaErrorInvalidValue;  // (the radix sort's scratch, which the caller hands over, is far larger)
+  e = exclusive_sum_u32(scan_temp, need, pairs, pair_start, m, st);
   if (e != cudaSuccess) return e;
   grid_table_init_kernel<<<(capacity + 255u) / 256u, 256, 0, st>>>(table, capacity);
-  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, grid_pts, table, capacity - 1u, d_max_count, curve);
+  grid_fill_kernel<<<(m + 255u) / 256u, 256, 0, st>>>(keys_sorted, vals_sorted, leaf_pts, m, pair_start, reinterpret_cast<GridPair*>(grid_pts), table, capacity - 1u, curve);
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count,
-                              const ChunkClasses& cc, cudaStream_t st) {
+cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, uint8_t* state,
+                              uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count, const ChunkClasses& cc, cudaStream_t st) {
   // *pending_count must be zero on entry: the previous probe (or the context) cleared it
-  const float cell = 1.0f / g.inv_cell;
   const uint32_t grid = (P.src.n + 255u) / 256u;
+  const GridPair* pairs = reinterpret_cast<const GridPair*>(grid_pts);
 #ifdef SGB_PROFILING
-  if (!blocks) {
-    grid_probe_kernel<4><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, cell * cell, state, pending_count, pending_list, pending_q, next_count);
-    return cudaGetLastError();
-  }
   static const int ctas = std::getenv("SGB_PROBE_CTAS") ? std::atoi(std::getenv("SGB_PROBE_CTAS")) : 5;
-  if (batch_tail) {
-    grid_probe_blocks_kernel<5, true><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
+  static const int unroll = std::getenv("SGB_PROBE_UNROLL") ? std::atoi(std::getenv("SGB_PROBE_UNROLL")) : 2;
+#define SGB_PROBE_VARIANT(C, U)                                                                                                                        \
+  if (ctas == C && unroll == U) {                                                                                                                      \
+    grid_probe_blocks_kernel<C, U><<<grid, 256, 0, st>>>(P, pairs, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc); \
+    return cudaGetLastError();                                                                                                                         \
+  }
+  static const bool prefetch = !(std::getenv("SGB_PROBE_PREFETCH") && std::getenv("SGB_PROBE_PREFETCH")[0] == '0');
+  if (!prefetch) {
+    grid_probe_blocks_kernel<5, 2, false><<<grid, 256, 0, st>>>(P, pairs, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
     return cudaGetLastError();
   }
-  if (ctas == 6) {
-    grid_probe_blocks_kernel<6, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
-    return cudaGetLastError();
-  }
-  if (ctas == 8) {
-    grid_probe_blocks_kernel<8, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
-    return cudaGetLastError();
-  }
-#else
-  (void)blocks;
-  (void)batch_tail;
-  (void)cell;
+  SGB_PROBE_VARIANT(5, 1) SGB_PROBE_VARIANT(5, 3) SGB_PROBE_VARIANT(5, 4) SGB_PROBE_VARIANT(6, 1) SGB_PROBE_VARIANT(6, 2) SGB_PROBE_VARIANT(6, 3) SGB_PROBE_VARIANT(8, 2)
+#undef SGB_PROBE_VARIANT
 #endif
-  grid_probe_blocks_kernel<5, false><<<grid, 256, 0, st>>>(P, grid_pts, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
+  grid_probe_blocks_kernel<5><<<grid, 256, 0, st>>>(P, pairs, table, capacity - 1u, g, state, pending_count, pending_list, pending_q, next_count, cc);
   return cudaGetLastError();
-}
-
-cudaError_t launch_ring_scan(const LinParams& P, const uint32_t* pending_count, const uint32_t* pending_list, uint32_t min_pending, const float4* grid_pts,
-                             const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid, cudaStream_t st) {
-#ifndef SGB_PROFILING
-  return cudaErrorNotSupported;
-#else
-  return launch_dependent(ring_scan_kernel, grid, 256, 0, st, P, pending_count, pending_list, min_pending, grid_pts, block_table, capacity - 1u, g, 1.0f / g.inv_cell);
-#endif
 }
 
 }  // namespace sgb

@@ -13,6 +13,22 @@ namespace sgb {
 // in cell units carries < 1e-3 of rounding error
 constexpr float kGridSlack = 4e-3f;
 
+// One entry of a block list: TWO points, components interleaved so that a 256-bit load brings both and packed FP32 arithmetic (f32x2)
+// computes both squared distances: a = (x0, x1, y0, y1), b = (z0, z1, leaf position 0, leaf position 1).  A list with an odd number of
+// points ends in a pad: coordinates kGridPadCoord (squared distance ~3e36: farther than anything real, still finite), position kNone.
+struct __align__(32) GridPair {
+  float4 a, b;
+};
+constexpr float kGridPadCoord = 1e18f;
+
+__device__ __forceinline__ GridPair load_pair(const GridPair* p) {
+  GridPair r;
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+      : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ uint64_t grid_key(int ix, int iy, int iz) {
   return (static_cast<uint64_t>(static_cast<uint32_t>(ix + (1 << 20)) & 0x1fffffu)) | (static_cast<uint64_t>(static_cast<uint32_t>(iy + (1 << 20)) & 0x1fffffu) << 21) |
          (static_cast<uint64_t>(static_cast<uint32_t>(iz + (1 << 20)) & 0x1fffffu) << 42);
@@ -64,12 +80,11 @@ __device__ __forceinline__ float grid_box_dist2(float qx, float qy, float qz, co
 struct RingParams {
   const uint32_t* list;     // pending list: source positions, [*count] entries
   const float4* q;          // parallel to it: transformed query (x, y, z) and the squared distance of the probe's best candidate (w)
-  const float4* grid_pts;   // block lists
+  const GridPair* grid_pairs;  // block lists (pair records)
   const GridSlot* table;    // block table (null: no ring phase, every pending query walks the tree)
   uint32_t mask;
   GridParams g;
   float cell;
-  bool few_only;            // the many-pending regime is somebody else's (profiling: ring_scan_kernel)
 };
 
 /// desc / dist: this warp's pending-subtree stack in shared memory (kPendStack entries each)
@@ -102,15 +117,16 @@ __device__ __forceinline__ void pending_search_body(const LinParams& P, const fl
         if ((ex * ex + ey * ey + ez * ez) * R.cell * R.cell < best_d) e = grid_lookup(R.table, R.mask, bx, by, bz);
       }
       // The (typically ~9 non-empty) lists are scanned as ONE flattened run spread over all 32 lanes: point j of the
-      // concatenation goes to lane j mod 32, which finds its list by a shuffle binary search over the exclusive prefix
+      // concatenation (of pair records) goes to lane j mod 32, which finds its list by a shuffle binary search over the exclusive prefix
       // sums of the counts.  A lane per list would walk up to ~40 points in dependent batches; this is ~7 loads per lane.
-      uint32_t incl = e.y;
+      const uint32_t np = (e.y + 1u) >> 1;  // records of this lane's list (two points each)
+      uint32_t incl = np;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= static_cast<uint32_t>(o)) incl += t;
       }
-      const uint32_t excl = incl - e.y, total = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t excl = incl - np, total = __shfl_sync(0xffffffffu, incl, 31);
       float my_d = best_d;
       uint32_t my_best = kNone;
 #pragma unroll 2
@@ -125,12 +141,17 @@ __device__ __forceinline__ void pending_search_body(const LinParams& P, const fl
         }
         const uint32_t st = __shfl_sync(0xffffffffu, e.x, owner), ex0 = __shfl_sync(0xffffffffu, excl, owner);
         if (j < total) {
-          const float4 t = __ldg(&R.grid_pts[st + (j - ex0)]);
-          const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
-          const float d = dx * dx + dy * dy + dz * dz;
-          if (d < my_d) {
-            my_d = d;
-            my_best = __float_as_uint(t.w);
+          const GridPair t = load_pair(R.grid_pairs + st + (j - ex0));
+          const float dx0 = t.a.x - qx, dy0 = t.a.z - qy, dz0 = t.b.x - qz;
+          const float dx1 = t.a.y - qx, dy1 = t.a.w - qy, dz1 = t.b.y - qz;
+          const float d0 = dx0 * dx0 + dy0 * dy0 + dz0 * dz0, d1 = dx1 * dx1 + dy1 * dy1 + dz1 * dz1;
+          if (d0 < my_d) {
+            my_d = d0;
+            my_best = __float_as_uint(t.b.z);
+          }
+          if (d1 < my_d) {  // (a pad never is: ~3e36)
+            my_d = d1;
+            my_best = __float_as_uint(t.b.w);
           }
         }
       }

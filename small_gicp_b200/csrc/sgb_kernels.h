@@ -93,30 +93,28 @@ struct __align__(16) GridSlot {
 struct PendingParams {
   const uint32_t* list;    // pending list (source positions)
   const float4* q;         // parallel: transformed query + squared distance of the probe's best candidate
-  const float4* grid_pts;  // block lists
+  const float4* grid_pts;  // block lists (pair records, sgb_grid.cuh)
   const GridSlot* table;   // block table, or null: no ring phase
   uint32_t capacity;
   GridParams g;
-  bool few_only;           // profiling (SGB_RING_SCAN=1): another kernel takes the many-pending regime, this launch only the few-pending one
 };
 /// queue / queue_next: two alternating zero-initialised counters of the dynamic chunk queue (this launch clears queue_next), or null = static stride.
 /// pending_count <= min_pending: the launch finishes the pending queries warp-per-query (ring phase / tree walk); more: the packet walk.
 cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int grid, int max_depth, const uint8_t* settled, const uint32_t* pending_count,
                                  uint32_t min_pending, uint32_t* queue, uint32_t* queue_next, const ChunkClasses& cc, const PendingParams& pp, bool tma_leaf, cudaStream_t st);
 cudaError_t launch_grid_spacing(const float4* pnodes, uint32_t n_inner, float* out, cudaStream_t st);
-cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, bool blocks, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in,
-                             uint32_t* vals_out, void* sort_temp, size_t sort_temp_bytes, uint32_t* d_distinct, bool curve, cudaStream_t st);
-cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, float4* grid_pts, GridSlot* table,
-                             uint32_t capacity, uint32_t* d_max_count, bool curve, cudaStream_t st);
+/// Block lists as PAIR RECORDS (sgb_grid.cuh: GridPair).  sort: keys of the 8 n entries, radix sort, then records per run at the run heads
+/// (into vals_in) and d_counters[0] = runs, [1] = longest run.  fill: exclusive scan (pairs -> pair_start), table, records.
+/// grid_pts must hold (m + runs) / 2 records of 32 B, i.e. (m + runs) float4.
+cudaError_t launch_grid_sort(const float4* leaf_pts, uint32_t n, const GridParams& g, uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
+                             void* sort_temp, size_t sort_temp_bytes, uint32_t* d_counters, bool curve, cudaStream_t st);
+cudaError_t launch_grid_fill(const uint64_t* keys_sorted, const uint32_t* vals_sorted, const float4* leaf_pts, uint32_t m, const uint32_t* pairs, uint32_t* pair_start,
+                             void* scan_temp, size_t scan_temp_bytes, float4* grid_pts, GridSlot* table, uint32_t capacity, bool curve, cudaStream_t st);
 /// longest list (points) the grid front end accepts: beyond it a single query's scan would dominate (a cluster of near-duplicate
 /// points, or a few far outliers stretching the box so that the cell-count bound inflates the cell) and the exact tree search alone is used
 constexpr uint32_t kGridMaxList = 2048;
-cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, bool blocks,
-                              bool batch_tail, uint8_t* state, uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count,
-                              const ChunkClasses& cc, cudaStream_t st);
-/// thread-per-query ring scan (many pending queries, rejector radius within the ring's reach); grid-stride
-cudaError_t launch_ring_scan(const LinParams& P, const uint32_t* pending_count, const uint32_t* pending_list, uint32_t min_pending, const float4* grid_pts,
-                             const GridSlot* block_table, uint32_t capacity, const GridParams& g, int grid, cudaStream_t st);
+cudaError_t launch_grid_probe(const LinParams& P, const float4* grid_pts, const GridSlot* table, uint32_t capacity, const GridParams& g, uint8_t* state,
+                              uint32_t* pending_count, uint32_t* pending_list, float4* pending_q, uint32_t* next_count, const ChunkClasses& cc, cudaStream_t st);
 /// what the 27-block ring is guaranteed to cover: squared radius ((2.5 - slack) cells)^2
 inline float ring_cover_sq(float cell) {
   const float c = (2.5f - 4e-3f) * cell;

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
       if (pc) pending_search_body(P, pnodes, pc, ring, s_child[threadIdx.x >> 5], s_dist + (threadIdx.x >> 5) * kPendStack);
       return;
     }
-    if (ring.few_only) return;
   }
   uint32_t tma_phase = 0;
   if (TMA_LEAF) {
@@ -300,12 +299,11 @@ cudaError_t launch_packet_search(const LinParams& P, const float4* pnodes, int g
   RingParams ring;
   ring.list = pp.list;
   ring.q = pp.q;
-  ring.grid_pts = pp.grid_pts;
+  ring.grid_pairs = reinterpret_cast<const GridPair*>(pp.grid_pts);
   ring.table = pp.table;
   ring.mask = pp.capacity ? pp.capacity - 1u : 0u;
   ring.g = pp.g;
   ring.cell = pp.g.inv_cell > 0.f ? 1.0f / pp.g.inv_cell : 0.f;
-  ring.few_only = pp.few_only;
 #ifdef SGB_PROFILING
   if (tma_leaf) {  // A/B (SGB_TMA_LEAF=1): leaf blocks staged by cp.async.bulk + mbarrier
     if (!settled) {

@@ -345,28 +345,24 @@ def test_search_structures_agree(synthetic_pair, monkeypatch):
     tc, tt, sc, Tgt, nt = synthetic_pair
     sg = _sg()
     results = {}
-    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_GRID_BLOCKS", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_PROBE_TAIL", "SGB_TMA_LEAF",
-                "SGB_CHUNK_CLASSES", "SGB_CLASS_FALLBACK_PCT", "SGB_RING_SCAN", "SGB_KD_SMEM")
+    switches = ("SGB_TREE", "SGB_SEARCH", "SGB_GRID", "SGB_RING", "SGB_PENDING_DIV", "SGB_GRID_CELL", "SGB_PACKET_QUEUE", "SGB_TMA_LEAF",
+                "SGB_CHUNK_CLASSES", "SGB_CLASS_FALLBACK_PCT", "SGB_KD_SMEM")
     for name, env, own in (
         ("device-kd/grid", {}, True),
         ("device-kd/no-grid", {"SGB_GRID": "0"}, True),
-        ("device-kd/grid-cells", {"SGB_GRID_BLOCKS": "0"}, True),
         ("device-kd/grid-no-ring", {"SGB_RING": "0"}, True),
         ("device-kd/grid-warp-per-pending", {"SGB_PENDING_DIV": "1"}, True),
-        ("device-kd/grid-ring-scan-pending", {"SGB_PENDING_DIV": "1000000", "SGB_RING_SCAN": "1"}, True),  # every pending query through the thread-per-query ring scan
         ("device-kd/grid-packet-pending", {"SGB_PENDING_DIV": "1000000"}, True),
         ("device-kd/grid-packet-pending-static-stride", {"SGB_PENDING_DIV": "1000000", "SGB_PACKET_QUEUE": "0"}, True),
         ("device-kd/no-grid-static-stride", {"SGB_GRID": "0", "SGB_PACKET_QUEUE": "0"}, True),
         ("device-kd/grid-small-cells", {"SGB_GRID_CELL": "0.7"}, True),
         ("device-kd/grid-small-cells-warp", {"SGB_GRID_CELL": "0.7", "SGB_PENDING_DIV": "1"}, True),
         ("device-kd/grid-large-cells", {"SGB_GRID_CELL": "6"}, True),
-        ("device-kd/grid-batched-tail", {"SGB_PROBE_TAIL": "1"}, True),
         ("device-kd/packet-tma-leaf", {"SGB_PENDING_DIV": "1000000", "SGB_TMA_LEAF": "1"}, True),
         ("device-kd/no-grid-tma-leaf", {"SGB_GRID": "0", "SGB_TMA_LEAF": "1"}, True),
         ("device-kd/packet-no-class-lists", {"SGB_PENDING_DIV": "1000000", "SGB_CHUNK_CLASSES": "0"}, True),
         ("device-kd/packet-class-lists-always", {"SGB_PENDING_DIV": "1000000", "SGB_CLASS_FALLBACK_PCT": "100"}, True),
         ("device-kd/packet-class-lists-never", {"SGB_PENDING_DIV": "1000000", "SGB_CLASS_FALLBACK_PCT": "0"}, True),
-        ("device-kd/grid-small-cells-ring-scan", {"SGB_GRID_CELL": "1.2", "SGB_PENDING_DIV": "1000000", "SGB_RING_SCAN": "1"}, True),
         ("device-lbvh/grid", {"SGB_TREE": "lbvh"}, True),
         ("device-kd-radix-levels/grid", {"SGB_KD_SMEM": "0"}, True),  # kd refinement with one radix sort per level all the way down
         ("device-kd-radix-levels/no-grid", {"SGB_KD_SMEM": "0", "SGB_GRID": "0"}, True),
@@ -415,8 +411,8 @@ def test_grid_far_and_unbounded_queries(synthetic_pair, monkeypatch):
         (Tgt, sg.REJECT_DISTANCE, 400.0),
     )
     out = {}
-    for name, env in (("grid", {}), ("tree", {"SGB_GRID": "0"}), ("grid-warp", {"SGB_PENDING_DIV": "1"}), ("grid-scan", {"SGB_PENDING_DIV": "1000000", "SGB_RING_SCAN": "1"}), ("grid-packet", {"SGB_PENDING_DIV": "1000000"})):
-        for k in ("SGB_GRID", "SGB_PENDING_DIV", "SGB_RING_SCAN"):
+    for name, env in (("grid", {}), ("tree", {"SGB_GRID": "0"}), ("grid-warp", {"SGB_PENDING_DIV": "1"}), ("grid-packet", {"SGB_PENDING_DIV": "1000000"})):
+        for k in ("SGB_GRID", "SGB_PENDING_DIV"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -427,7 +423,7 @@ def test_grid_far_and_unbounded_queries(synthetic_pair, monkeypatch):
             res.append((H, e, ctx.correspondences(), ctx.num_inliers()))
         out[name] = res
         ctx.close()
-    for name in ("grid", "grid-warp", "grid-scan", "grid-packet"):
+    for name in ("grid", "grid-warp", "grid-packet"):
         for k, ((H, e, c, ni), (H0, e0, c0, ni0)) in enumerate(zip(out[name], out["tree"])):
             assert (c != c0).sum() <= 3, (name, k, int((c != c0).sum()))
             assert abs(ni - ni0) <= 3, (name, k)
