@@ -14,6 +14,9 @@ what = {"UBLKCP": "`cp.async.bulk` (TMA 1-D bulk copy): leaf staging A/B of the 
         "LDGSTS": "`cp.async` (factor kernel's two-tiles-ahead operand pipeline)", "ACQBULK": "`griddepcontrol.wait` (programmatic dependent launch of kernels 2-4)",
         "REDUX": "warp-wide integer min / max (`__reduce_min_sync`: nearest point of a leaf / a ring in one instruction)",
         "DFMA": "FP64 fused multiply-add (factor algebra, sums)", "SHFL": "warp shuffles (transposing reduction, query broadcast)", "VOTE": "warp votes (divergence-free packet walk)",
+        "LDG.E.ENL2.256": "256-bit global loads (`ld.global.nc.v8.f32`, new with sm_100): one pair record of a block list per load (probe, ring search)",
+        "FFMA2": "packed FP32 fma (`fma.rn.f32x2`, new with sm_100): both squared distances of a pair record at once", "FADD2": "packed FP32 add (query - point, two points)",
+        "FMUL2": "packed FP32 multiply",
         "ATOMG": "global atomics (work queues, pending / class lists, tickets)", "MEMBAR": "fences (ticket tree, peer mailboxes)", "LDG.E.128": "128-bit global loads (float4 SoA streams)"}
 sass = {}
 for lib in ("libsgicp_b200.so", "libsgicp_b200_prof.so"):
