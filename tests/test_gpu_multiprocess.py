@@ -21,5 +21,10 @@ def test_fused_allreduce_across_processes(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
            os.path.join(ROOT, "tests", "mp_fused_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    if r.returncode != 0:  # torchrun's own summary buries the worker's traceback: keep everything, show the lines that name the error
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"mp_fused_check_world{world}.log"), "w") as f:
+            f.write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+    culprit = [ln for ln in r.stderr.splitlines() if ("Error" in ln or "assert" in ln) and "ChildFailedError" not in ln][:20]
+    assert r.returncode == 0, "\n".join(culprit) + "\n" + r.stderr[-1500:]
     assert "mp_fused_check ok" in r.stdout
