@@ -121,12 +121,16 @@ int build_grid(sgb_ctx* ctx) {
                         ctx->stream));
   CU(ctx->sort_temp.reserve(tb));
   uint32_t* d_distinct = ctx->grid_pending.as<uint32_t>();  // the two pending counters double as scratch during construction
-  uint32_t* d_max_list = d_distinct + 1;
   CU(launch_grid_sort(ctx->tgt_pts.as<float4>(), static_cast<uint32_t>(n), g, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
                       ctx->vals_in.as<uint32_t>(), ctx->pre_vals_out.as<uint32_t>(), ctx->sort_temp.p, tb, d_distinct, ctx->grid_curve_order, ctx->stream));
-  uint32_t distinct = 0;
-  CU(cudaMemcpyAsync(&distinct, d_distinct, sizeof(distinct), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->pending_clean = false;  // the two counters of the construction live in the pending counters
+  uint32_t counters[2] = {0, 0};  // runs (= lists), longest run
+  CU(cudaMemcpyAsync(counters, d_distinct, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const uint32_t distinct = counters[0], max_list = counters[1];
+  ctx->launches += 4;
+  if (ctx->debug_pending) std::fprintf(stderr, "[sgb] grid front end: cell %.4g, %u distinct lists, longest %u points\n", cell, distinct, max_list);
+  if (max_list > kGridMaxList) return 0;  // degenerate density (see kGridMaxList): the tree search alone stays exact and bounded
   uint32_t capacity = 1024;
   while (capacity < 2ull * distinct) capacity <<= 1;  // load factor <= 1/2
   CU(ctx->grid_table.reserve(static_cast<size_t>(capacity) * sizeof(GridSlot)));
@@ -136,13 +140,7 @@ int build_grid(sgb_ctx* ctx) {
                       ctx->keys_in.as<uint32_t>(), ctx->sort_temp.p, tb, ctx->grid_pts.as<float4>(), ctx->grid_table.as<GridSlot>(), capacity, ctx->grid_curve_order,
                       ctx->stream));
   ctx->grid_blocks = true;
-  ctx->pending_clean = false;  // d_distinct / d_max_list live in the pending counters
-  ctx->launches += 9;
-  uint32_t max_list = 0;
-  CU(cudaMemcpyAsync(&max_list, d_max_list, sizeof(max_list), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (ctx->debug_pending) std::fprintf(stderr, "[sgb] grid front end: cell %.4g, %u distinct lists, longest %u points\n", cell, distinct, max_list);
-  if (max_list > kGridMaxList) return 0;  // degenerate density (see kGridMaxList): the tree search alone stays exact and bounded
+  ctx->launches += 5;
   for (int a = 0; a < 3; a++) ctx->grid_origin[a] = g.origin[a];
   ctx->grid_inv_cell = g.inv_cell;
   ctx->grid_settle_d2 = g.settle_d2;

@@ -80,7 +80,7 @@ struct sgb_ctx {
   sgb::DevBuf pre_boxes;
   size_t n_pnodes = 0;      // packet records of the current target tree
   // uniform-grid front end of the search (sgb_grid.cu)
-  bool use_grid = true, grid_ready = false, grid_blocks = true;  // grid_blocks: 2 x 2 x 2 block lists (one lookup per query) instead of per-cell lists
+  bool use_grid = true, grid_ready = false, grid_blocks = true;  // grid_blocks: the front end holds 2 x 2 x 2 block lists (one lookup per query)
   sgb::DevBuf grid_pts, grid_table, grid_state, grid_spacing, grid_pending;  // grid_pending: [0], [1] = alternating counters, [2..] = pending query positions
   sgb::DevBuf grid_pending_q;  // parallel to the list: transformed query + squared distance of the probe's best candidate
   bool use_ring = true, debug_pending = false;  // profiling switches (sgb_create)

@@ -5,18 +5,17 @@
 // spacing away.  The 2 x 2 x 2 block of grid cells (cell edge c) anchored at floor(u - 1/2) covers the cube
 // [q - c/2, q + c/2]^3, i.e. it holds EVERY target point within c/2 of q: if the closest point of the block is within c/2
 // it is the exact nearest neighbour and the query is finished -- no tree walk, no dependent pointer chasing.
-//   * BLOCK LISTS (default): every target point is stored under the eight blocks that contain its cell, so a block is
-//     ONE hash lookup and ONE contiguous run of points (grid_probe_blocks_kernel).  8x the point storage buys the removal
-//     of seven lookups and of the divergent per-cell scans.
-//   * per-cell lists (SGB_GRID_BLOCKS=0, kept for the A/B in profiles/r01): eight lookups, own cell first, the other
-//     cells pruned by their box distance (grid_probe_kernel).
+// BLOCK LISTS: every target point is stored under the eight blocks that contain its cell, so a block is ONE hash lookup and ONE
+// contiguous run of points (grid_probe_blocks_kernel); 8x the point storage buys the removal of seven lookups and of divergent per-cell
+// scans (round 1 A/B, profiles/r01).  The runs are stored as 32-byte PAIR RECORDS (sgb_grid.cuh: GridPair): one 256-bit load and packed
+// FP32 arithmetic per two points (profiles/r02/b_experiments.md).
 // Queries the probe cannot settle (nothing within c/2: misaligned first iterations, holes, outliers) are appended to a
-// compact pending list -- with the best candidate found so far as an upper bound -- and finished exactly:
-//   * few of them: a warp per query (pending_search_kernel): ring search over the 27 blocks at stride 2 around the query
+// compact pending list -- with the best candidate found so far as an upper bound -- and finished exactly by packet_search_kernel:
+//   * few of them: a warp per query (pending_search_body, sgb_grid.cuh): ring search over the 27 blocks at stride 2 around the query
 //     (everything within 2.5 c), then, only if that radius does not decide it, a walk of the packet tree;
-//   * many of them: the packet search (sgb_kernels_packet.cu) over the chunk-ordered queries, settled lanes idle.
+//   * many of them: the packet walk (sgb_kernels_packet.cu) over the chunk-ordered queries, settled lanes idle.
 // Which of the two runs is decided on the device from the pending counter.  Results are identical to a pure tree search
-// (exact ties aside; tests/test_gpu_parity.py::test_search_structures_agree); evidence and A/B runs: profiles/r01.
+// (exact ties aside; tests/test_gpu_parity.py::test_search_structures_agree); evidence and A/B runs: profiles/r01, profiles/r02.
 #include <cfloat>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
@@ -86,7 +85,8 @@ __global__ void grid_heads_kernel(const uint64_t* __restrict__ keys, uint32_t m,
     head = i == 0 || keys[i - 1] != k;
     if (head) {
       uint32_t cnt = 1;
-      while (i + cnt < m && keys[i + cnt] == k) cnt++;
+      // (a run longer than the front end accepts is only measured up to the limit: build_grid drops the grid before anything reads the records)
+      while (i + cnt < m && cnt <= kGridMaxList && keys[i + cnt] == k) cnt++;
       np = (cnt + 1u) >> 1;
       atomicMax(counters + 1, cnt);  // longest list: build_grid drops the front end when one query would have to scan thousands of points
     }
