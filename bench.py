@@ -517,27 +517,33 @@ def run_c5(B, sizes):
             setup_s = time.perf_counter() - t0
             row = {"points": n, "points_per_gpu": hi - lo, "setup_s": setup_s}
             reps = 10 if n <= 10_000_000 else 5
-            for name, T in (("iteration0", np.eye(4)), ("converged", Tgt)):
-                def step():
-                    ctx.drop_seeds()
-                    ctx.linearize_device(T, B.out.data_ptr(), factor=sg.FACTOR_GICP, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0)
-                    if B.use_dist and not fused:
-                        B.dist.all_reduce(B.out[:44])
+            for fname, fkind in (("GICP", sg.FACTOR_GICP), ("ICP", sg.FACTOR_ICP)):  # both factors
+                for name, T in (("iteration0", np.eye(4)), ("converged", Tgt)):
+                    def step():
+                        ctx.drop_seeds()
+                        ctx.linearize_device(T, B.out.data_ptr(), factor=fkind, rejector=sg.REJECT_DISTANCE, max_dist_sq=1.0)
+                        if B.use_dist and not fused:
+                            B.dist.all_reduce(B.out[:44])
 
-                for _ in range(2):
-                    step()
-                ms = B.event_ms(step, reps)
-                gbs = BYTES_PER_POINT["GICP"] * (n / B.world) / (ms * 1e-3) / 1e9  # per GPU
-                row[name] = {"ms": ms, "mpoints_per_s": n / (ms * 1e-3) / 1e6, "algorithmic_gbs_per_gpu": gbs, "roofline_frac": gbs / peak}
-            h = B.out[:44].cpu().numpy()
-            row["inliers_converged"] = int(round(h[43]))
+                    for _ in range(2):
+                        step()
+                    ms = B.event_ms(step, reps)
+                    gbs = BYTES_PER_POINT[fname] * (n / B.world) / (ms * 1e-3) / 1e9  # per GPU
+                    res = {"ms": ms, "mpoints_per_s": n / (ms * 1e-3) / 1e6, "algorithmic_gbs_per_gpu": gbs, "roofline_frac": gbs / peak}
+                    if fname == "GICP":
+                        row[name] = res
+                    else:
+                        row.setdefault("icp", {})[name] = res
+                if fname == "GICP":
+                    h = B.out[:44].cpu().numpy()
+                    row["inliers_converged"] = int(round(h[43]))
             rows.append(row)
         finally:
             B.barrier()
             ctx.close()
             torch.cuda.empty_cache()
     return {
-        "what": "BASELINE configs[4]: linearize (GICP, DistanceRejector(1.0)) over N target x N source points, density constant; ONE source strong-sharded over the GPUs (slabs along x), target + kd-tree + block lists replicated; clouds generated and prepared on the device (kd-tree, k=20 covariances); unseeded search; CUDA events, L2 flushed, max over ranks",
+        "what": "BASELINE configs[4]: linearize (GICP; `icp` = the same with the point-to-point factor, 36 algorithmic B / point; DistanceRejector(1.0)) over N target x N source points, density constant; ONE source strong-sharded over the GPUs (slabs along x), target + kd-tree + block lists replicated; clouds generated and prepared on the device (kd-tree, k=20 covariances); unseeded search; CUDA events, L2 flushed, max over ranks",
         "n_gpus": B.world,
         "rows": rows,
     }
