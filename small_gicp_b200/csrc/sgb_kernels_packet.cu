@@ -179,7 +179,6 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
           const unsigned closer_l = __ballot_sync(0xffffffffu, (wl || wr) && dl <= dr);
           const bool left_first = 2 * __popc(closer_l) >= __popc(ml | mr);
           my_dist[sp * kLinBlock] = left_first ? dr : dl;
-          __syncwarp();  // every lane is done reading the entry a previous pop left at this depth (write-after-read on my_child[sp])
           if (lane == 0) my_child[sp] = left_first ? make_uint2(__float_as_uint(n2.w), __float_as_uint(n3.w)) : make_uint2(__float_as_uint(n0.w), __float_as_uint(n1.w));
           sp++;
           ca = left_first ? __float_as_uint(n0.w) : __float_as_uint(n2.w);
@@ -211,8 +210,9 @@ __global__ void __launch_bounds__(kLinBlock, MIN_CTAS) packet_search_kernel(cons
           sp--;
           const float d = my_dist[sp * kLinBlock];
           if (__any_sync(0xffffffffu, d < best_d)) {
-            __syncwarp();
+            __syncwarp();  // lane 0's push of this entry is visible
             c = my_child[sp];
+            __syncwarp();  // ... and every lane has read it before lane 0 may push over it (entries popped unread need neither)
             leaf_d = d;
             got = true;
             break;
