@@ -143,10 +143,9 @@ __global__ void grid_table_init_kernel(GridSlot* table, uint32_t capacity) {
 // ---------------------------------------------------------------------------------------------------------------
 // probe, block lists: the block anchored at floor(u - 1/2) covers [q - c/2, q + c/2]^3; one lookup, one contiguous scan
 // ---------------------------------------------------------------------------------------------------------------
-// BATCH_TAIL (A/B switch SGB_PROBE_TAIL=1; measured once at the end of round 1: no gain, stays off -- profiles/r01/am_linearize.md): the plain loop below is unrolled by 8, which leaves a
-// remainder loop of count % 8 iterations with ONE load in flight each -- 15 % of the kernel's stall samples sit on that
-// load's first use (profiles/r01/am).  The batched form always issues eight loads, clamping the index to the last point of
-// the list: a repeated point can never be strictly closer than itself, so the result is unchanged.
+// UNROLL pairs of the scan loop are in flight per thread (2: 32 registers = 8 CTAs of 256 threads = full occupancy, measured best: r02aa / r02ab);
+// PREFETCH: the whole list is requested into L2 as soon as its table slot is known (-6 us).  MIN_CTAS / UNROLL / PREFETCH other than the defaults
+// exist in the profiling library only (SGB_PROBE_CTAS, SGB_PROBE_UNROLL, SGB_PROBE_PREFETCH).
 template <int MIN_CTAS, int UNROLL = 2, bool PREFETCH = true>
 __global__ void __launch_bounds__(256, MIN_CTAS) grid_probe_blocks_kernel(const __grid_constant__ LinParams P, const GridPair* __restrict__ grid_pairs,
                                                                const GridSlot* __restrict__ table, uint32_t mask, GridParams g, uint8_t* state,
